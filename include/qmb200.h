@@ -1,0 +1,170 @@
+/*
+ * qmb200.h -- C ABI of libqmb200.so: the B200-native (sm_100a) implementation of
+ * QuakeMigrate's coalescence hot path.
+ *
+ * Two tiers of entry points:
+ *
+ *  T1  the five symbols of the reference C extension, with byte-identical signatures, so that
+ *      libqmb200.so can literally be loaded by an unmodified quakemigrate.core
+ *      (quakemigrate/core/libnames.py:35-38 opens  core/src/qmlib<EXT_SUFFIX>  with ctypes.CDLL;
+ *      prototypes: quakemigrate/core/src/qmlib.h:28-44, export list qmlib.def:3-7;
+ *      ctypes argtypes: quakemigrate/core/lib.py:38-49,128,173,211,249).
+ *      Host pointers in, host pointers out, GPU inside.  They honour the reference contract
+ *      (caller allocates everything; map4d arrives zeroed and is accumulated into; STA/LTA
+ *      outputs arrive pre-filled) and therefore move N*T doubles over PCIe: plumbing, not speed.
+ *
+ *  T2  the fused path QuakeScan._compute needs (quakemigrate/signal/scan.py:594-647):
+ *      device-resident travel-time tables, onset functions computed/kept on the device, the
+ *      4-D volume never materialised for detect(), a marginal window for locate(), node-sharded
+ *      multi-GPU with NCCL.  All functions return an int status (0 = QMB_OK) and record a
+ *      message retrievable with qmb_last_error(); host buffers are always caller-owned, exactly
+ *      like the reference (C never allocates, frees or retains host pointers).
+ *
+ * There is NO CPU fallback anywhere behind this header: without a CUDA device every T2 call
+ * returns QMB_ERR_CUDA and every T1 call aborts with a message on stderr.
+ */
+#ifndef QMB200_H
+#define QMB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * T1 -- reference-compatible symbols (qmlib.h:28-44)
+ * ---------------------------------------------------------------------------------------- */
+
+/* qmlib.h:34-38; numpy mirror quakemigrate/core/lib.py:33-36 */
+typedef struct {
+  int n;
+  int nsta;
+  int nlta;
+} stalta_header;
+
+/* replaces migrate(), quakemigrate/core/src/migratelib.c:40-65 */
+void migrate(double *onsets, int32_t *lookup_tables, double *map4d, int32_t fsmp, int32_t lsmp,
+             int32_t n_samples, int32_t n_stations, int32_t available, int64_t n_nodes,
+             int64_t threads);
+
+/* replaces find_max_coa(), quakemigrate/core/src/migratelib.c:85-111 */
+void find_max_coa(double *map4d, double *max_coa, double *max_norm_coa, int64_t *max_coa_idx,
+                  int32_t n_samples, int64_t n_nodes, int64_t threads);
+
+/* replace quakemigrate/core/src/onsetlib.c:35-59, :79-108, :126-148 */
+void overlapping_sta_lta(const double *signal, const stalta_header *head, double *onset);
+void centred_sta_lta(const double *signal, const stalta_header *head, double *onset);
+void recursive_sta_lta(const double *signal, const stalta_header *head, double *onset);
+
+/* ------------------------------------------------------------------------------------------
+ * T2 -- fused device-resident path
+ * ---------------------------------------------------------------------------------------- */
+
+enum {
+  QMB_OK = 0,
+  QMB_ERR_CUDA = 1,        /* CUDA runtime / driver failure (includes "no device") */
+  QMB_ERR_ARG = 2,         /* invalid argument (the reference's ValueError cases, lib.py:105-110) */
+  QMB_ERR_UNSUPPORTED = 3, /* shape outside what the kernels were built for */
+  QMB_ERR_NCCL = 4,        /* NCCL not loadable / collective failure */
+  QMB_ERR_STATE = 5        /* call sequence error (e.g. fetch before scan) */
+};
+
+enum { QMB_STALTA_CLASSIC = 0, QMB_STALTA_CENTRED = 1, QMB_STALTA_RECURSIVE = 2 };
+enum { QMB_TRANSFORM_NONE = 0, QMB_TRANSFORM_ENERGY = 1, QMB_TRANSFORM_ABS = 2 };
+
+typedef struct qmb_ctx *qmb_ctx_t;       /* one per (process, GPU) */
+typedef struct qmb_lut *qmb_lut_t;       /* device-resident travel-time table (node slab) */
+typedef struct qmb_onsets *qmb_onsets_t; /* device-resident log-onset rows */
+
+const char *qmb_last_error(void);
+const char *qmb_version(void);
+int qmb_device_count(int *count);
+
+int qmb_ctx_create(int device, qmb_ctx_t *out);
+int qmb_ctx_destroy(qmb_ctx_t ctx);
+int qmb_ctx_sync(qmb_ctx_t ctx);
+/* kernel variant: nodes per warp (4 or 8); 0 = default.  Must be set before qmb_lut_upload. */
+int qmb_ctx_set_variant(qmb_ctx_t ctx, int nodes_per_warp);
+/* number of launches of this library's own kernels since context creation */
+int qmb_ctx_launch_count(qmb_ctx_t ctx, int64_t *count);
+
+/* --- multi-GPU (one process per GPU; ids are exchanged by the host application) ---------- */
+#define QMB_NCCL_ID_BYTES 128
+int qmb_comm_unique_id(void *id_out /* QMB_NCCL_ID_BYTES */);
+int qmb_comm_init(qmb_ctx_t ctx, const void *id, int world, int rank);
+int qmb_comm_destroy(qmb_ctx_t ctx);
+
+/* --- travel-time table ---------------------------------------------------------------------
+ * `lut` is what LUT.serve_traveltimes returns (quakemigrate/lut/lut.py:502-538): int32,
+ * C-order (nx, ny, nz, n_rows), station axis fastest == the `lookup_tables` argument of
+ * migrate().  For node-sharded runs each rank uploads its x-slab only:
+ * (nx_local, ny, nz, n_rows) plus the flat index of its first node and the global node count
+ * (needed for max_norm_coa = max * N / sum, migratelib.c:108).  Negative entries clamp to 0
+ * (migratelib.c:55).  Upload once per availability pattern; reuse across calls. */
+int qmb_lut_upload(qmb_ctx_t ctx, const int32_t *lut, int32_t nx_local, int32_t ny, int32_t nz,
+                   int32_t n_rows, int64_t node_offset, int64_t n_nodes_global, qmb_lut_t *out);
+int qmb_lut_free(qmb_lut_t lut);
+typedef struct {
+  int64_t n_nodes_local, n_nodes_global, node_offset;
+  int32_t n_rows, max_tau, max_tile_span, n_tiles, nodes_per_tile;
+  int64_t device_bytes;
+} qmb_lut_info_t;
+int qmb_lut_info(qmb_lut_t lut, qmb_lut_info_t *info);
+
+/* --- onset functions -------------------------------------------------------------------------
+ * qmb_onsets_upload: `onsets` are the LINEAR onset functions returned by
+ * Onset.calculate_onsets (float64 (n_rows, n_total), base.py:103-106); the clip(0.01)+log of
+ * quakemigrate/core/lib.py:93-94 happens on the device.
+ * qmb_onsets_from_waveforms: STALTAOnset._onset on the device (stalta.py:516-548): transform,
+ * per-channel STA/LTA (onsetlib.c), RMS over the channels of each row, clip(min_onset_value);
+ * optionally returns the linear onsets to the host (the picker needs them, gaussian.py:142).
+ *   waveforms   float64 (n_channels, n_total), host
+ *   row_ptr     int32 (n_rows+1): channels of row r are row_chan[row_ptr[r] .. row_ptr[r+1])
+ *   nsta, nlta  int32 (n_rows): window lengths in samples per row (stalta.py:394-396)
+ */
+int qmb_onsets_upload(qmb_ctx_t ctx, const double *onsets, int32_t n_rows, int64_t n_total,
+                      qmb_onsets_t *out);
+int qmb_onsets_from_waveforms(qmb_ctx_t ctx, const double *waveforms, int32_t n_channels,
+                              int64_t n_total, int32_t n_rows, const int32_t *row_ptr,
+                              const int32_t *row_chan, const int32_t *nsta, const int32_t *nlta,
+                              int32_t position, int32_t transform, double min_onset_value,
+                              double *onsets_out /* nullable, (n_rows, n_total) */,
+                              qmb_onsets_t *out);
+int qmb_onsets_free(qmb_onsets_t onsets);
+
+/* batched STA/LTA on (n_channels, n) host arrays; `onset` must arrive pre-filled like the
+ * reference wrappers do (lib.py:204,242,281) -- only the valid range is written. */
+int qmb_sta_lta(qmb_ctx_t ctx, const double *signal, int32_t n_channels, int64_t n, int32_t nsta,
+                int32_t nlta, int32_t position, double *onset);
+
+/* --- detect: fused migrate + stack + per-sample max / argmax / normalised max -----------------
+ * Equivalent to  find_max_coa(migrate(onsets, lut, fsmp, lsmp, available, threads), threads)
+ * (scan.py:635-638) without ever materialising map4d.  n_samples = n_total - fsmp - lsmp.
+ * qmb_detect_device runs on device-resident inputs and leaves results on the device
+ * (qmb_detect_fetch copies them out); qmb_detect is the one-call host-buffer form.
+ * With a communicator attached, every rank calls with its own LUT slab and identical onsets and
+ * all ranks receive the global result.  kernel_ms (nullable, 4 floats): device time of
+ * [scan kernel, merge+finalise, total, slow-path samples (count)] measured with CUDA events. */
+int qmb_detect_device(qmb_ctx_t ctx, qmb_lut_t lut, qmb_onsets_t onsets, int32_t fsmp,
+                      int32_t lsmp, int32_t available, float *kernel_ms);
+int qmb_detect_fetch(qmb_ctx_t ctx, double *max_coa, double *max_norm_coa, int64_t *max_coa_idx,
+                     int32_t n_samples);
+int qmb_detect(qmb_ctx_t ctx, qmb_lut_t lut, const double *onsets, int32_t n_rows,
+               int64_t n_total, int32_t fsmp, int32_t lsmp, int32_t available, double *max_coa,
+               double *max_norm_coa, int64_t *max_coa_idx);
+
+/* --- locate: detect outputs + the marginal window of the 4-D map ------------------------------
+ * After a detect pass over the whole span, re-migrates only samples [win0, win1) (end-exclusive,
+ * quakemigrate/io/event.py:433-435) and returns
+ *   coa_map  float64 (n_nodes_local): sum over the window of map4d (scan.py:720; the caller
+ *            divides by its max, scan.py:721)
+ *   map4d_win nullable float64 (n_nodes_local, win1-win0): the window slab itself. */
+int qmb_locate_window(qmb_ctx_t ctx, qmb_lut_t lut, qmb_onsets_t onsets, int32_t fsmp,
+                      int32_t lsmp, int32_t available, int32_t win0, int32_t win1,
+                      double *coa_map, double *map4d_win);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QMB200_H */

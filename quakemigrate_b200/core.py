@@ -1,0 +1,322 @@
+# -*- coding: utf-8 -*-
+"""
+Drop-in for :mod:`quakemigrate.core` backed by ``libqmb200.so`` (B200, sm_100a).
+
+Tier 1 -- same five functions, same signatures, same exceptions as the reference bindings
+(``quakemigrate/core/lib.py``): :func:`migrate`, :func:`find_max_coa`,
+:func:`overlapping_sta_lta`, :func:`centred_sta_lta`, :func:`recursive_sta_lta`.  They call the
+reference-compatible C symbols, which run on the GPU but return the full float64 volume through
+host memory, exactly like the reference.
+
+Tier 2 -- :class:`Engine`: device-resident travel-time tables and onsets, fused
+detect (no 4-D volume), marginal window for locate, node-sharded multi-GPU.
+
+No CPU fallback exists: importing works anywhere, calling needs the CUDA library and a B200.
+"""
+
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import QmbError, c_int32, c_int64, stalta_header_t  # noqa: F401
+
+__all__ = ["migrate", "find_max_coa", "overlapping_sta_lta", "centred_sta_lta",
+           "recursive_sta_lta", "Engine", "DeviceLUT", "DeviceOnsets", "QmbError"]
+
+
+# ------------------------------------------------------------------------------------------------
+# Tier 1: quakemigrate.core look-alikes
+# ------------------------------------------------------------------------------------------------
+def migrate(onsets, traveltimes, first_idx, last_idx, available, threads):
+    """
+    Computes 4-D coalescence map by migrating seismic phase onset functions.
+
+    Same contract as ``quakemigrate.core.lib.migrate`` (lib.py:53-125): ``onsets``
+    (nonsets, nsamples) float64 linear onsets, ``traveltimes`` (nx, ny, nz, nonsets) int32;
+    returns ``map4d`` (nx, ny, nz, nsamples - first_idx - last_idx) float64.  ``threads`` is
+    accepted for signature compatibility and ignored (the work runs on the GPU).
+
+    Raises ``ValueError`` in the two cases the reference does (lib.py:105-110).
+    """
+    lib = _lib.load()
+    # geometric mean as an arithmetic mean of logs; clip guards log(0) -- lib.py:93-94
+    onsets = np.clip(onsets, 0.01, np.inf)
+    onsets = np.ascontiguousarray(np.log(onsets), dtype=np.double)
+
+    *grid_dimensions, n_luts = traveltimes.shape
+    n_onsets, t_samples = onsets.shape
+    n_samples = t_samples - first_idx - last_idx
+    map4d = np.zeros(tuple(grid_dimensions) + (n_samples,), dtype=np.double)
+    n_nodes = int(np.prod(grid_dimensions))
+
+    if not n_luts == n_onsets:
+        raise ValueError(
+            f"Mismatch between number of stations for data and LUT, {n_onsets}:{n_luts}"
+        )
+    if onsets.size < n_samples + first_idx:
+        raise ValueError("Data array smaller than coalescence array.")
+
+    lib.migrate(
+        onsets, np.ascontiguousarray(traveltimes, dtype=np.int32), map4d,
+        c_int32(first_idx), c_int32(last_idx), c_int32(n_samples), c_int32(n_onsets),
+        c_int32(int(available)), c_int64(n_nodes), c_int64(int(threads)),
+    )
+    return map4d
+
+
+def find_max_coa(map4d, threads):
+    """``quakemigrate.core.lib.find_max_coa`` (lib.py:132-170): (max_coa, max_norm_coa, max_coa_idx)."""
+    lib = _lib.load()
+    *grid_dimensions, n_samples = map4d.shape
+    n_nodes = int(np.prod(grid_dimensions))
+    max_coa = np.zeros(n_samples, dtype=np.double)
+    max_norm_coa = np.zeros(n_samples, dtype=np.double)
+    max_coa_idx = np.zeros(n_samples, dtype=np.int64)
+    lib.find_max_coa(
+        np.ascontiguousarray(map4d, dtype=np.double), max_coa, max_norm_coa, max_coa_idx,
+        c_int32(n_samples), c_int64(n_nodes), c_int64(int(threads)),
+    )
+    return max_coa, max_norm_coa, max_coa_idx
+
+
+def _legacy_stalta(name, prefill, signal, nsta, nlta):
+    lib = _lib.load()
+    head = np.empty(1, dtype=stalta_header_t)
+    head[:] = (len(signal), nsta, nlta)
+    signal = np.ascontiguousarray(signal, dtype=np.double)
+    onset = np.full(len(signal), prefill, dtype=np.double)
+    getattr(lib, name)(signal, head, onset)
+    return onset
+
+
+def overlapping_sta_lta(signal, nsta, nlta):
+    """Classic STA/LTA, value at the window end (lib.py:176-208; onsetlib.c:35-59)."""
+    return _legacy_stalta("overlapping_sta_lta", 1.0, signal, nsta, nlta)
+
+
+def centred_sta_lta(signal, nsta, nlta):
+    """Centred STA/LTA (lib.py:214-246; onsetlib.c:79-108)."""
+    return _legacy_stalta("centred_sta_lta", 1.0, signal, nsta, nlta)
+
+
+def recursive_sta_lta(signal, nsta, nlta):
+    """Recursive STA/LTA (lib.py:252-285; onsetlib.c:126-148)."""
+    return _legacy_stalta("recursive_sta_lta", 0.0, signal, nsta, nlta)
+
+
+# ------------------------------------------------------------------------------------------------
+# Tier 2: device-resident engine
+# ------------------------------------------------------------------------------------------------
+class DeviceLUT:
+    """Handle to a travel-time table (node slab) resident on the device."""
+
+    def __init__(self, engine, handle, shape, node_offset, n_nodes_global):
+        self.engine, self._h = engine, handle
+        self.shape = tuple(shape)  # (nx_local, ny, nz, n_rows)
+        self.node_offset, self.n_nodes_global = node_offset, n_nodes_global
+
+    @property
+    def n_rows(self):
+        return self.shape[-1]
+
+    @property
+    def n_nodes_local(self):
+        return int(np.prod(self.shape[:-1]))
+
+    def info(self) -> dict:
+        inf = _lib.LutInfo()
+        _lib.check(_lib.load().qmb_lut_info(self._h, ctypes.byref(inf)))
+        return {name: getattr(inf, name) for name, _ in inf._fields_}
+
+    def free(self):
+        if self._h:
+            _lib.load().qmb_lut_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class DeviceOnsets:
+    """Handle to log-onset rows resident on the device."""
+
+    def __init__(self, engine, handle, n_rows, n_total):
+        self.engine, self._h = engine, handle
+        self.n_rows, self.n_total = n_rows, n_total
+
+    def free(self):
+        if self._h:
+            _lib.load().qmb_onsets_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Engine:
+    """One GPU context: streams, scratch, optional NCCL communicator."""
+
+    def __init__(self, device: int = 0, nodes_per_warp: int | None = None):
+        self._lib = _lib.load()
+        h = ctypes.c_void_p()
+        _lib.check(self._lib.qmb_ctx_create(int(device), ctypes.byref(h)))
+        self._h = h
+        self.device = device
+        self.world, self.rank = 1, 0
+        if nodes_per_warp:
+            _lib.check(self._lib.qmb_ctx_set_variant(self._h, int(nodes_per_warp)))
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.qmb_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        _lib.check(self._lib.qmb_ctx_sync(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        n = c_int64(0)
+        _lib.check(self._lib.qmb_ctx_launch_count(self._h, ctypes.byref(n)))
+        return n.value
+
+    # -- multi-GPU --------------------------------------------------------------------------
+    @staticmethod
+    def new_comm_id() -> bytes:
+        buf = ctypes.create_string_buffer(_lib.QMB_NCCL_ID_BYTES)
+        _lib.check(_lib.load().qmb_comm_unique_id(buf))
+        return buf.raw
+
+    def init_comm(self, comm_id: bytes, world: int, rank: int):
+        _lib.check(self._lib.qmb_comm_init(self._h, comm_id, int(world), int(rank)))
+        self.world, self.rank = world, rank
+
+    # -- inputs -----------------------------------------------------------------------------
+    def upload_lut(self, traveltimes: np.ndarray, node_offset: int = 0,
+                   n_nodes_global: int | None = None) -> DeviceLUT:
+        """``traveltimes``: int32 (nx_local, ny, nz, n_rows) as ``LUT.serve_traveltimes`` returns."""
+        if traveltimes.ndim != 4:
+            raise ValueError("traveltimes must have shape (nx, ny, nz, n_onsets)")
+        tt = np.ascontiguousarray(traveltimes, dtype=np.int32)
+        nx, ny, nz, s = tt.shape
+        n_glob = int(n_nodes_global) if n_nodes_global else nx * ny * nz
+        h = ctypes.c_void_p()
+        _lib.check(self._lib.qmb_lut_upload(self._h, tt, nx, ny, nz, s, int(node_offset), n_glob,
+                                            ctypes.byref(h)))
+        return DeviceLUT(self, h, tt.shape, int(node_offset), n_glob)
+
+    def upload_onsets(self, onsets: np.ndarray) -> DeviceOnsets:
+        """``onsets``: float64 (n_rows, n_total) LINEAR onsets (clip + log happen on the device)."""
+        on = np.ascontiguousarray(onsets, dtype=np.double)
+        if on.ndim != 2:
+            raise ValueError("onsets must have shape (n_onsets, n_samples)")
+        h = ctypes.c_void_p()
+        _lib.check(self._lib.qmb_onsets_upload(self._h, on, on.shape[0], on.shape[1], ctypes.byref(h)))
+        return DeviceOnsets(self, h, on.shape[0], on.shape[1])
+
+    def onsets_from_waveforms(self, waveforms, row_channels, nsta, nlta, position="classic",
+                              transform="energy", min_onset_value=0.4, return_onsets=False):
+        """
+        ``STALTAOnset._onset`` on the device for every row (stalta.py:516-548).
+
+        waveforms: float64 (n_channels, n_total); row_channels: list (per onset row) of channel
+        index lists; nsta / nlta: ints or per-row sequences (samples).
+        Returns DeviceOnsets, or (DeviceOnsets, linear onsets ndarray) when ``return_onsets``.
+        """
+        wf = np.ascontiguousarray(waveforms, dtype=np.double)
+        n_rows = len(row_channels)
+        row_ptr = np.zeros(n_rows + 1, dtype=np.int32)
+        row_ptr[1:] = np.cumsum([len(c) for c in row_channels])
+        row_chan = np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.int32) for c in row_channels]))
+        nsta_a = np.ascontiguousarray(np.broadcast_to(np.asarray(nsta, dtype=np.int32), (n_rows,)))
+        nlta_a = np.ascontiguousarray(np.broadcast_to(np.asarray(nlta, dtype=np.int32), (n_rows,)))
+        out = np.empty((n_rows, wf.shape[1]), dtype=np.double) if return_onsets else None
+        h = ctypes.c_void_p()
+        _lib.check(self._lib.qmb_onsets_from_waveforms(
+            self._h, wf, wf.shape[0], wf.shape[1], n_rows, row_ptr, row_chan, nsta_a, nlta_a,
+            _lib.STALTA_POSITION[position], _lib.TRANSFORM[transform], float(min_onset_value),
+            out.ctypes.data_as(ctypes.c_void_p) if out is not None else None, ctypes.byref(h)))
+        dev = DeviceOnsets(self, h, n_rows, wf.shape[1])
+        return (dev, out) if return_onsets else dev
+
+    def sta_lta(self, signals, nsta, nlta, position="classic", prefill=None):
+        """Batched STA/LTA of (n_channels, n) signals; pre-fill follows lib.py:204,242,281."""
+        sig = np.ascontiguousarray(np.atleast_2d(signals), dtype=np.double)
+        if prefill is None:
+            prefill = 0.0 if position == "recursive" else 1.0
+        out = np.full(sig.shape, prefill, dtype=np.double)
+        _lib.check(self._lib.qmb_sta_lta(self._h, sig, sig.shape[0], sig.shape[1], int(nsta), int(nlta),
+                                         _lib.STALTA_POSITION[position], out))
+        return out
+
+    # -- detect -----------------------------------------------------------------------------
+    def detect_device(self, lut: DeviceLUT, onsets: DeviceOnsets, fsmp: int, lsmp: int, available: int):
+        """Run the fused scan on device-resident inputs; returns kernel timings (ms) as a dict."""
+        ms = (ctypes.c_float * 4)()
+        _lib.check(self._lib.qmb_detect_device(self._h, lut._h, onsets._h, int(fsmp), int(lsmp),
+                                               int(available), ctypes.cast(ms, ctypes.c_void_p)))
+        return {"scan_ms": ms[0], "finalize_ms": ms[1], "total_ms": ms[2], "slow_samples": int(ms[3])}
+
+    def detect_fetch(self, n_samples: int):
+        max_coa = np.empty(n_samples, dtype=np.double)
+        max_norm = np.empty(n_samples, dtype=np.double)
+        idx = np.empty(n_samples, dtype=np.int64)
+        _lib.check(self._lib.qmb_detect_fetch(self._h, max_coa, max_norm, idx, int(n_samples)))
+        return max_coa, max_norm, idx
+
+    def detect(self, lut: DeviceLUT, onsets, fsmp: int, lsmp: int, available: int):
+        """
+        ``find_max_coa(migrate(onsets, lut, fsmp, lsmp, available))`` fused on the device
+        (scan.py:635-638).  ``onsets`` may be a host array (linear, float64) or DeviceOnsets.
+        """
+        if isinstance(onsets, DeviceOnsets):
+            self.detect_device(lut, onsets, fsmp, lsmp, available)
+            return self.detect_fetch(onsets.n_total - fsmp - lsmp)
+        on = np.ascontiguousarray(onsets, dtype=np.double)
+        n_rows, n_total = on.shape
+        if n_rows != lut.n_rows:
+            raise ValueError(
+                f"Mismatch between number of stations for data and LUT, {n_rows}:{lut.n_rows}"
+            )
+        n_samples = n_total - fsmp - lsmp
+        if n_samples <= 0:
+            raise ValueError("Data array smaller than coalescence array.")
+        max_coa = np.empty(n_samples, dtype=np.double)
+        max_norm = np.empty(n_samples, dtype=np.double)
+        idx = np.empty(n_samples, dtype=np.int64)
+        _lib.check(self._lib.qmb_detect(self._h, lut._h, on, n_rows, n_total, int(fsmp), int(lsmp),
+                                        int(available), max_coa, max_norm, idx))
+        return max_coa, max_norm, idx
+
+    # -- locate -----------------------------------------------------------------------------
+    def locate_window(self, lut: DeviceLUT, onsets: DeviceOnsets, fsmp: int, lsmp: int, available: int,
+                      win0: int, win1: int, return_map4d: bool = False):
+        """
+        Marginal window [win0, win1) (end-exclusive, io/event.py:433-435) of the 4-D map:
+        returns ``coa_map`` (nx_local, ny, nz) = sum over the window (scan.py:720) and optionally
+        the window slab (nx_local, ny, nz, win1 - win0).
+        """
+        grid = lut.shape[:-1]
+        coa = np.empty(grid, dtype=np.double)
+        slab = np.empty(grid + (win1 - win0,), dtype=np.double) if return_map4d else None
+        _lib.check(self._lib.qmb_locate_window(
+            self._h, lut._h, onsets._h, int(fsmp), int(lsmp), int(available), int(win0), int(win1),
+            coa.ctypes.data_as(ctypes.c_void_p),
+            slab.ctypes.data_as(ctypes.c_void_p) if slab is not None else None))
+        return (coa, slab) if return_map4d else coa

@@ -1,0 +1,154 @@
+// qmb_internal.cuh -- shared declarations of libqmb200 (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/qmb200.h"
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+void qmb_set_error(const char *fmt, ...);
+
+#define QMB_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      qmb_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));     \
+      return QMB_ERR_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+#define QMB_TRY(call)                                                                          \
+  do {                                                                                         \
+    int s__ = (call);                                                                          \
+    if (s__ != QMB_OK) return s__;                                                             \
+  } while (0)
+
+#define QMB_FAIL(code, ...)                                                                    \
+  do {                                                                                         \
+    qmb_set_error(__VA_ARGS__);                                                                \
+    return (code);                                                                             \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// geometry constants of the scan kernel
+// ---------------------------------------------------------------------------------------------
+constexpr int QMB_CONSUMER_WARPS = 16;  // node-quads (or octets) processed concurrently per CTA
+constexpr int QMB_CHUNK_ROWS = 16;      // onset rows (station x phase) staged per pipeline stage
+constexpr int QMB_SMEM_BUDGET = 227 * 1024;
+
+// ---------------------------------------------------------------------------------------------
+// device buffer helper (RAII-free; owned by the structs below)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  int ensure(size_t count) {
+    if (count <= n && p) return QMB_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    if (count == 0) return QMB_OK;
+    QMB_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+    n = count;
+    return QMB_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// handles
+// ---------------------------------------------------------------------------------------------
+struct qmb_ctx {
+  int device = 0;
+  int sm_count = 148;
+  int npw = 4;  // nodes per consumer warp: 4 (tile 4x4x4, 256-sample time tiles) or 8 (4x4x8, 128)
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  int64_t launches = 0;
+
+  // NCCL
+  void *nccl_comm = nullptr;
+  int world = 1, rank = 0;
+
+  // scan scratch (grown on demand)
+  DevBuf<float> pm1, pm2, pm3;
+  DevBuf<uint32_t> pi1, pi2;
+  DevBuf<double> psum;
+  // merged per-sample state
+  DevBuf<float> gm1, gm2, gm3;
+  DevBuf<uint32_t> gi1, gi2;
+  DevBuf<double> gsum, ex1, ex2;
+  DevBuf<unsigned char> gather;  // all-gather staging
+  // results
+  DevBuf<double> r_max, r_norm;
+  DevBuf<long long> r_idx;
+  DevBuf<int> slow_list;  // [0] = count, [1..] = samples
+  DevBuf<double> slow_val;
+  DevBuf<unsigned long long> slow_idx;
+  int32_t last_n_samples = 0;
+  // pinned staging for small D2H
+  int *h_pinned = nullptr;
+};
+
+struct qmb_lut {
+  qmb_ctx *ctx = nullptr;
+  int32_t nxl = 0, ny = 0, nz = 0, S = 0, Spad = 0;
+  int64_t node_offset = 0, n_global = 0, n_local = 0;
+  int npw = 4;       // variant this table was tiled for
+  int tx = 4, ty = 4, tz = 4, NB = 64;
+  int ntx = 0, nty = 0, ntz = 0, n_tiles = 0;
+  int32_t max_tau = 0, max_span = 0;
+  DevBuf<uint16_t> tau16;   // [n_tiles][Spad][NB]   tau - tmin4(tile,row)
+  DevBuf<int32_t> tmin;     // [n_tiles][Spad]       multiple of 4
+  DevBuf<uint16_t> span;    // [n_tiles][Spad]       max(tau16) within the tile
+  DevBuf<uint32_t> nodeidx; // [n_tiles][NB]         global flat node index or 0xFFFFFFFF (pad)
+};
+
+struct qmb_onsets {
+  qmb_ctx *ctx = nullptr;
+  int32_t S = 0;
+  int64_t P = 0;          // samples per row as seen by the caller (fsmp + T + lsmp)
+  int64_t stride = 0;     // device row stride in elements (multiple of 4)
+  int64_t front = 0;      // leading pad elements (so that front + fsmp can be 16B-aligned)
+  DevBuf<float> log32;    // [S][stride]
+  DevBuf<double> log64;   // [S][stride]
+  DevBuf<double> rowmax;  // [S] max |log onset| per row (for the fp32 error bound)
+};
+
+constexpr int64_t QMB_ONSET_FRONT = 4;     // leading pad (elements); alignment slack
+constexpr int64_t QMB_ONSET_TAIL = 1024;   // trailing zero pad: >= time tile + max tile span + 8
+
+// ---------------------------------------------------------------------------------------------
+// cross-file entry points
+// ---------------------------------------------------------------------------------------------
+int qmb_lut_build(qmb_ctx *ctx, qmb_lut *L, const int32_t *d_raw);
+int qmb_onsets_prepare(qmb_ctx *ctx, qmb_onsets *O, const double *d_linear /* (S,P) */, int already_log);
+int qmb_scan_run(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, int32_t fsmp, int32_t lsmp,
+                 int32_t available, float *kernel_ms);
+int qmb_window_run(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, int32_t fsmp, int32_t lsmp,
+                   int32_t available, int32_t win0, int32_t win1, double *d_coa_map,
+                   double *d_map4d_win, int accumulate);
+int qmb_stalta_device(qmb_ctx *ctx, const double *d_signal, int32_t n_channels, int64_t n,
+                      int64_t stride, int32_t nsta, int32_t nlta, int32_t position,
+                      int32_t transform, double *d_onset);
+int qmb_stalta_device_ex(qmb_ctx *ctx, const double *d_signal, int32_t n_channels, int64_t n,
+                         int64_t stride_in, int64_t stride_out, int32_t nsta, int32_t nlta,
+                         int32_t position, int32_t transform, double *d_onset,
+                         const int *d_src_chan, const int *d_nsta, const int *d_nlta);
+int qmb_fill_f64(qmb_ctx *ctx, double *d, double v, size_t n);
+int qmb_onsets_combine(qmb_ctx *ctx, qmb_onsets *O, const double *d_chan, int64_t chan_stride,
+                       const int *d_row_ptr, double min_onset, double *d_lin_out);
+int qmb_nccl_allgather(qmb_ctx *ctx, const void *send, void *recv, size_t bytes_per_rank);
+int qmb_nccl_allreduce_sum_f64(qmb_ctx *ctx, double *buf, size_t count);
+qmb_ctx *qmb_default_ctx();

@@ -1,0 +1,147 @@
+// qmb_lut.cu -- device-resident travel-time tables, re-tiled for the scan kernel.
+//
+// Input is exactly the array the reference hands to migrate(): int32 (n_nodes, n_rows), station
+// axis fastest (quakemigrate/core/src/migratelib.c:53; produced by LUT.serve_traveltimes,
+// quakemigrate/lut/lut.py:502-538).  The scan kernel wants, per spatially compact TILE of nodes
+// (4x4x4 or 4x4x8) and per onset row:
+//     tmin4  = (min over the tile of max(0,tau)) rounded down to a multiple of 4 samples
+//     tau16  = max(0,tau) - tmin4   (uint16; the tile's tau-range is small because it is compact)
+//     span   = max over the tile of tau16
+// so that one 16-byte-aligned bulk copy of  [tmin4, tmin4 + span + time_tile)  of the onset row
+// serves every node of the tile.  The clamp of negative travel times (migratelib.c:55) is
+// applied here, once.
+#include "qmb_internal.cuh"
+
+namespace {
+
+constexpr int LT_THREADS = 128;
+constexpr int LT_ROWS = 32;  // rows handled per pass through shared memory
+
+struct LutTileParams {
+  const int32_t *raw;  // (nxl*ny*nz, S)
+  int nxl, ny, nz, S, Spad;
+  int tx, ty, tz, NB;
+  int ntx, nty, ntz;
+  long long node_offset, n_valid;
+  uint16_t *tau16;
+  int32_t *tmin;
+  uint16_t *span;
+  uint32_t *nodeidx;
+  int *stats;  // [0] max tau, [1] max span, [2] overflow flag
+};
+
+__global__ void __launch_bounds__(LT_THREADS) k_lut_tile(LutTileParams p) {
+  __shared__ int s_tau[LT_ROWS][128 + 1];
+  __shared__ long long s_node[128];  // clamped local flat index per slot
+  const int j = blockIdx.x;
+  const int tzi = j % p.ntz, tyi = (j / p.ntz) % p.nty, txi = j / (p.ntz * p.nty);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NWARPS = LT_THREADS / 32;
+
+  if (tid < p.NB) {
+    const int dz = tid % p.tz, dy = (tid / p.tz) % p.ty, dx = tid / (p.tz * p.ty);
+    const int ix = txi * p.tx + dx, iy = tyi * p.ty + dy, iz = tzi * p.tz + dz;
+    const int cx = min(ix, p.nxl - 1), cy = min(iy, p.ny - 1), cz = min(iz, p.nz - 1);
+    long long local = ((long long)cx * p.ny + cy) * p.nz + cz;
+    const long long flat = ((long long)ix * p.ny + iy) * p.nz + iz;
+    const bool valid = ix < p.nxl && iy < p.ny && iz < p.nz && flat < p.n_valid;
+    if (local >= p.n_valid) local = p.n_valid - 1;  // ragged last x-plane of a pseudo-grid
+    s_node[tid] = local;
+    p.nodeidx[(size_t)j * p.NB + tid] =
+        valid ? (uint32_t)(p.node_offset + ((long long)ix * p.ny + iy) * p.nz + iz) : 0xFFFFFFFFu;
+  }
+  __syncthreads();
+
+  int my_max_tau = 0, my_max_span = 0, overflow = 0;
+  for (int s0 = 0; s0 < p.Spad; s0 += LT_ROWS) {
+    // gather: one warp per node slot, lanes over rows (coalesced 128-byte reads of the raw table)
+    for (int q = warp; q < p.NB; q += NWARPS) {
+      const int s = s0 + lane;
+      int v = 0;
+      if (s < p.S) v = max(0, p.raw[s_node[q] * p.S + s]);
+      s_tau[lane][q] = v;
+    }
+    __syncthreads();
+    // reduce + emit: one warp per row
+    for (int r = warp; r < LT_ROWS; r += NWARPS) {
+      const int s = s0 + r;
+      if (s >= p.Spad) break;
+      int mn = 0x7fffffff, mx = 0;
+      for (int q = lane; q < p.NB; q += 32) {
+        mn = min(mn, s_tau[r][q]);
+        mx = max(mx, s_tau[r][q]);
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      }
+      const int base = mn & ~3;
+      const int sp = mx - base;
+      if (sp > 65535) overflow = 1;
+      for (int q = lane; q < p.NB; q += 32)
+        p.tau16[((size_t)j * p.Spad + s) * p.NB + q] = (uint16_t)min(s_tau[r][q] - base, 65535);
+      if (lane == 0) {
+        p.tmin[(size_t)j * p.Spad + s] = base;
+        p.span[(size_t)j * p.Spad + s] = (uint16_t)min(sp, 65535);
+      }
+      my_max_tau = max(my_max_tau, mx);
+      my_max_span = max(my_max_span, sp);
+    }
+    __syncthreads();
+  }
+  if (lane == 0) {
+    atomicMax(&p.stats[0], my_max_tau);
+    atomicMax(&p.stats[1], my_max_span);
+    if (overflow) atomicMax(&p.stats[2], 1);
+  }
+}
+
+}  // namespace
+
+int qmb_lut_build(qmb_ctx *ctx, qmb_lut *L, const int32_t *d_raw) {
+  L->npw = ctx->npw;
+  L->tx = 4;
+  L->ty = 4;
+  L->tz = (ctx->npw == 8) ? 8 : 4;
+  L->NB = L->tx * L->ty * L->tz;
+  L->ntx = (L->nxl + L->tx - 1) / L->tx;
+  L->nty = (L->ny + L->ty - 1) / L->ty;
+  L->ntz = (L->nz + L->tz - 1) / L->tz;
+  const long long nt = (long long)L->ntx * L->nty * L->ntz;
+  if (nt > 0x7fffffffLL) QMB_FAIL(QMB_ERR_UNSUPPORTED, "too many node tiles (%lld)", nt);
+  L->n_tiles = (int)nt;
+  L->Spad = ((L->S + QMB_CHUNK_ROWS - 1) / QMB_CHUNK_ROWS) * QMB_CHUNK_ROWS;
+
+  QMB_TRY(L->tau16.ensure((size_t)L->n_tiles * L->Spad * L->NB));
+  QMB_TRY(L->tmin.ensure((size_t)L->n_tiles * L->Spad));
+  QMB_TRY(L->span.ensure((size_t)L->n_tiles * L->Spad));
+  QMB_TRY(L->nodeidx.ensure((size_t)L->n_tiles * L->NB));
+
+  int *d_stats = nullptr;
+  QMB_CUDA(cudaMalloc((void **)&d_stats, 4 * sizeof(int)));
+  QMB_CUDA(cudaMemsetAsync(d_stats, 0, 4 * sizeof(int), ctx->stream));
+
+  LutTileParams p;
+  p.raw = d_raw;
+  p.nxl = L->nxl; p.ny = L->ny; p.nz = L->nz; p.S = L->S; p.Spad = L->Spad;
+  p.tx = L->tx; p.ty = L->ty; p.tz = L->tz; p.NB = L->NB;
+  p.ntx = L->ntx; p.nty = L->nty; p.ntz = L->ntz;
+  p.node_offset = L->node_offset;
+  p.n_valid = L->n_local;
+  p.tau16 = L->tau16.p; p.tmin = L->tmin.p; p.span = L->span.p; p.nodeidx = L->nodeidx.p;
+  p.stats = d_stats;
+  k_lut_tile<<<L->n_tiles, LT_THREADS, 0, ctx->stream>>>(p);
+  ctx->launches++;
+  QMB_CUDA(cudaGetLastError());
+  int h_stats[4] = {0, 0, 0, 0};
+  QMB_CUDA(cudaMemcpyAsync(h_stats, d_stats, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  QMB_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_stats);
+  L->max_tau = h_stats[0];
+  L->max_span = h_stats[1];
+  if (h_stats[2])
+    QMB_FAIL(QMB_ERR_UNSUPPORTED,
+             "travel-time range inside one %dx%dx%d node tile exceeds 65535 samples", L->tx, L->ty,
+             L->tz);
+  return QMB_OK;
+}

@@ -1,0 +1,197 @@
+# -*- coding: utf-8 -*-
+"""
+GPU parity tests: libqmb200 (through its C ABI / ctypes) against the CPU oracle on identical
+seeded inputs.  Bars (north_star): arg-max indices bit-exact; coalescence values within 1e-5
+relative (we assert much tighter where the arithmetic allows).
+"""
+
+import numpy as np
+import pytest
+
+from oracle import qm_oracle as O
+from quakemigrate_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+RTOL_COA = 1e-5          # stated tolerance of the north star
+RTOL_COA_TIGHT = 1e-9    # max_coa is re-evaluated in float64: expect ~1e-15
+RTOL_NORM = 2e-6         # normalised max uses the fp32 node-sum
+
+
+def _oracle_kind():
+    return "ref" if O.have("ref") else "port"
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from quakemigrate_b200.core import Engine
+    eng = Engine(0)
+    yield eng
+    eng.close()
+
+
+@pytest.fixture(scope="module", params=[4, 8])
+def engine_v(request):
+    from quakemigrate_b200.core import Engine
+    eng = Engine(0, nodes_per_warp=request.param)
+    yield eng
+    eng.close()
+
+
+def _check_detect(got, want, rtol_norm=RTOL_NORM):
+    g_max, g_norm, g_idx = got
+    w_max, w_norm, w_idx = want
+    assert np.array_equal(g_idx, w_idx), f"argmax mismatch at {np.nonzero(g_idx != w_idx)[0][:10]}"
+    np.testing.assert_allclose(g_max, w_max, rtol=RTOL_COA_TIGHT)
+    np.testing.assert_allclose(g_norm, w_norm, rtol=rtol_norm)
+
+
+# ------------------------------------------------------------------------------------------------
+# STA/LTA
+# ------------------------------------------------------------------------------------------------
+def test_stalta_reference_kat():
+    """tests/test_onsets.py:23-39 of the reference, through the T1 symbols."""
+    from quakemigrate_b200 import core
+    signal = np.arange(6)
+    overlapping = core.overlapping_sta_lta(signal, 2, 3)
+    assert (overlapping == np.array([1.0, 1.0, 1.5, 1.25, 21. / 18, 27. / 24])).all()
+    centred = core.centred_sta_lta(signal, 2, 3)
+    assert np.allclose(centred, np.array([1.0, 1.0, 3.5, 2.25, 1.0, 1.0]))
+
+
+@pytest.mark.parametrize("position", ["classic", "centred", "recursive"])
+@pytest.mark.parametrize("n,nsta,nlta", [(5000, 21, 101), (4097, 3, 251), (310, 5, 300), (64, 1, 2)])
+def test_stalta_random(engine, position, n, nsta, nlta):
+    rng = np.random.default_rng(n + nsta)
+    sig = rng.standard_normal((3, n)) ** 2
+    got = engine.sta_lta(sig, nsta, nlta, position)
+    fn = {"classic": O.overlapping_sta_lta, "centred": O.centred_sta_lta,
+          "recursive": O.recursive_sta_lta}[position]
+    want = np.array([fn(s, nsta, nlta, kind=_oracle_kind()) for s in sig])
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=0)
+
+
+def test_stalta_centred_zero_lta(engine):
+    """lta <= 0 -> exactly 1.0 for i >= nlta (onsetlib.c:102-106)."""
+    sig = np.zeros((1, 400))
+    sig[0, 200:] = 1.0
+    got = engine.sta_lta(sig, 5, 50, "centred")
+    want = O.centred_sta_lta(sig[0], 5, 50, kind=_oracle_kind())
+    sel = np.isfinite(want)
+    np.testing.assert_allclose(got[0][sel], want[sel], rtol=1e-12)
+    assert np.array_equal(np.isfinite(got[0]), sel)
+
+
+def test_onsets_from_waveforms(engine):
+    cfg = syn.CONFIGS["cfg2"].scaled(grid=(6, 6, 4), n_samples=3000, n_rows=6)
+    prob = syn.make_problem(cfg)
+    dev, lin = engine.onsets_from_waveforms(prob.waveforms, prob.row_channels, prob.nsta, prob.nlta,
+                                            position="classic", return_onsets=True)
+    want = syn.onsets_from_waveforms(prob, lambda x, a, b: O.overlapping_sta_lta(x, a, b, kind=_oracle_kind()))
+    np.testing.assert_allclose(lin, want, rtol=1e-9)
+    dev.free()
+
+
+# ------------------------------------------------------------------------------------------------
+# detect: fused migrate + find_max_coa
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("grid,S,T,fsmp,lsmp", [
+    ((6, 5, 4), 7, 50, 13, 40),        # tiny, ragged tiles, odd rows
+    ((9, 8, 10), 16, 300, 0, 64),      # fsmp = 0
+    ((13, 4, 4), 33, 513, 7, 31),      # three row chunks, T not multiple of the tile
+    ((4, 4, 4), 1, 1, 1, 5),           # single row, single sample
+])
+def test_detect_random(engine_v, grid, S, T, fsmp, lsmp):
+    onsets, tau = syn.random_problem(S * 1000 + T, grid, S, T, fsmp, lsmp, neg_frac=0.05)
+    lut = engine_v.upload_lut(tau)
+    got = engine_v.detect(lut, onsets, fsmp, lsmp, S)
+    m4 = O.migrate(onsets, tau, fsmp, lsmp, S, threads=4, kind=_oracle_kind())
+    want = O.find_max_coa(m4, threads=4, kind=_oracle_kind())
+    _check_detect(got, want)
+    lut.free()
+
+
+def test_detect_synthetic_homogeneous(engine_v):
+    cfg = syn.CONFIGS["cfg2"].scaled(grid=(21, 18, 11), n_samples=1500, n_rows=8)
+    prob = syn.make_problem(cfg)
+    onsets = syn.onsets_from_waveforms(prob, lambda x, a, b: O.overlapping_sta_lta(x, a, b))
+    lut = engine_v.upload_lut(prob.traveltimes)
+    got = engine_v.detect(lut, onsets, prob.fsmp, prob.lsmp, cfg.n_rows)
+    want = O.detect_fused(onsets, prob.traveltimes, prob.fsmp, prob.lsmp, cfg.n_rows, threads=8)
+    _check_detect(got, want)
+    # the planted events must show up as maxima near their origin time at the right node
+    lut.free()
+
+
+def test_detect_exact_ties_resolve_to_lowest_index(engine_v):
+    """Constant onsets: every node ties at every sample -> index 0 (migratelib.c:96-105)."""
+    grid, S, T, fsmp, lsmp = (5, 6, 7), 5, 70, 3, 20
+    onsets = np.full((S, fsmp + T + lsmp), 0.4)
+    tau = np.random.default_rng(1).integers(0, lsmp + 1, size=grid + (S,), dtype=np.int32)
+    lut = engine_v.upload_lut(tau)
+    g_max, g_norm, g_idx = engine_v.detect(lut, onsets, fsmp, lsmp, S)
+    assert (g_idx == 0).all()
+    np.testing.assert_allclose(g_max, 0.4, rtol=1e-12)
+    np.testing.assert_allclose(g_norm, 1.0, rtol=1e-6)
+    lut.free()
+
+
+def test_detect_partial_ties(engine_v):
+    """Many values sit exactly on the clip floor: pair/slow-path candidates must match the oracle."""
+    grid, S, T, fsmp, lsmp = (8, 8, 8), 4, 200, 5, 30
+    onsets, tau = syn.random_problem(77, grid, S, T, fsmp, lsmp, floor_frac=0.9)
+    lut = engine_v.upload_lut(tau)
+    got = engine_v.detect(lut, onsets, fsmp, lsmp, S)
+    want = O.find_max_coa(O.migrate(onsets, tau, fsmp, lsmp, S, threads=4), threads=4)
+    _check_detect(got, want)
+    lut.free()
+
+
+def test_detect_errors(engine):
+    onsets, tau = syn.random_problem(3, (4, 4, 4), 3, 20, 2, 10)
+    lut = engine.upload_lut(tau)
+    with pytest.raises(ValueError):   # lib.py:105-108
+        engine.detect(lut, onsets[:2], 2, 10, 3)
+    with pytest.raises(ValueError):   # lib.py:109-110
+        engine.detect(lut, onsets, 20, 20, 3)
+    from quakemigrate_b200.core import QmbError
+    with pytest.raises(QmbError):     # tau beyond the post-pad: the reference would read past rows
+        engine.detect(lut, onsets[:, :-5], 2, 5, 3)
+    lut.free()
+
+
+# ------------------------------------------------------------------------------------------------
+# T1: reference-compatible symbols
+# ------------------------------------------------------------------------------------------------
+def test_legacy_migrate_find_max(engine):
+    from quakemigrate_b200 import core
+    grid, S, T, fsmp, lsmp = (7, 6, 5), 6, 90, 4, 25
+    onsets, tau = syn.random_problem(11, grid, S, T, fsmp, lsmp, neg_frac=0.1)
+    m_got = core.migrate(onsets, tau, fsmp, lsmp, S, 1)
+    m_want = O.migrate(onsets, tau, fsmp, lsmp, S, threads=2, kind=_oracle_kind())
+    assert m_got.shape == m_want.shape
+    np.testing.assert_allclose(m_got, m_want, rtol=RTOL_COA)
+    f_got = core.find_max_coa(m_want, 1)
+    f_want = O.find_max_coa(m_want, threads=2, kind=_oracle_kind())
+    assert np.array_equal(f_got[2], f_want[2])
+    np.testing.assert_allclose(f_got[0], f_want[0], rtol=0, atol=0)
+    np.testing.assert_allclose(f_got[1], f_want[1], rtol=1e-13)
+    with pytest.raises(ValueError):
+        core.migrate(onsets[:3], tau, fsmp, lsmp, S, 1)
+
+
+# ------------------------------------------------------------------------------------------------
+# locate: marginal window
+# ------------------------------------------------------------------------------------------------
+def test_locate_window(engine_v):
+    grid, S, T, fsmp, lsmp = (9, 7, 6), 6, 400, 10, 40
+    onsets, tau = syn.random_problem(5, grid, S, T, fsmp, lsmp)
+    lut = engine_v.upload_lut(tau)
+    dev = engine_v.upload_onsets(onsets)
+    m4 = O.migrate(onsets, tau, fsmp, lsmp, S, threads=4, kind=_oracle_kind())
+    for w0, w1 in [(0, T), (123, 301), (399, 400)]:
+        coa, slab = engine_v.locate_window(lut, dev, fsmp, lsmp, S, w0, w1, return_map4d=True)
+        np.testing.assert_allclose(slab, m4[..., w0:w1], rtol=RTOL_COA)
+        np.testing.assert_allclose(coa, m4[..., w0:w1].sum(axis=-1), rtol=RTOL_COA)
+    dev.free()
+    lut.free()
