@@ -89,6 +89,12 @@ int qmb_ctx_set_variant(qmb_ctx_t ctx, int nodes_per_warp);
 /* number of launches of this library's own kernels since context creation */
 int qmb_ctx_launch_count(qmb_ctx_t ctx, int64_t *count);
 
+/* benchmarking helpers: evict L2 by writing a 256 MiB scratch buffer; page-lock caller memory
+ * so that H2D/D2H copies of host buffers run at full PCIe rate (cudaHostRegister). */
+int qmb_ctx_flush_l2(qmb_ctx_t ctx);
+int qmb_host_register(void *ptr, int64_t bytes);
+int qmb_host_unregister(void *ptr);
+
 /* --- multi-GPU (one process per GPU; ids are exchanged by the host application) ---------- */
 #define QMB_NCCL_ID_BYTES 128
 int qmb_comm_unique_id(void *id_out /* QMB_NCCL_ID_BYTES */);

@@ -72,6 +72,9 @@ SIGNATURES = {
     "qmb_ctx_sync": (ctypes.c_int, [c_void_p]),
     "qmb_ctx_set_variant": (ctypes.c_int, [c_void_p, ctypes.c_int]),
     "qmb_ctx_launch_count": (ctypes.c_int, [c_void_p, ctypes.POINTER(c_int64)]),
+    "qmb_ctx_flush_l2": (ctypes.c_int, [c_void_p]),
+    "qmb_host_register": (ctypes.c_int, [c_void_p, c_int64]),
+    "qmb_host_unregister": (ctypes.c_int, [c_void_p]),
     "qmb_comm_unique_id": (ctypes.c_int, [ctypes.c_char_p]),
     "qmb_comm_init": (ctypes.c_int, [c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]),
     "qmb_comm_destroy": (ctypes.c_int, [c_void_p]),

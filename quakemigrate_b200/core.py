@@ -165,15 +165,17 @@ class DeviceOnsets:
 class Engine:
     """One GPU context: streams, scratch, optional NCCL communicator."""
 
-    def __init__(self, device: int = 0, nodes_per_warp: int | None = None):
+    def __init__(self, device: int = 0, variant: int | None = None):
         self._lib = _lib.load()
         h = ctypes.c_void_p()
         _lib.check(self._lib.qmb_ctx_create(int(device), ctypes.byref(h)))
         self._h = h
         self.device = device
         self.world, self.rank = 1, 0
-        if nodes_per_warp:
-            _lib.check(self._lib.qmb_ctx_set_variant(self._h, int(nodes_per_warp)))
+        if variant is not None:
+            # kernel tiling variant (consumer warps x nodes per warp x samples per lane), see
+            # QMB_VARIANTS in csrc/qmb_internal.cuh; applies to tables uploaded afterwards
+            _lib.check(self._lib.qmb_ctx_set_variant(self._h, int(variant)))
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self):
@@ -195,6 +197,19 @@ class Engine:
         n = c_int64(0)
         _lib.check(self._lib.qmb_ctx_launch_count(self._h, ctypes.byref(n)))
         return n.value
+
+    def flush_l2(self):
+        """Evict L2 (benchmark hygiene between timed iterations)."""
+        _lib.check(self._lib.qmb_ctx_flush_l2(self._h))
+
+    @staticmethod
+    def pin(array: np.ndarray):
+        """Page-lock a host array in place (cudaHostRegister) so copies run at PCIe rate."""
+        _lib.check(_lib.load().qmb_host_register(array.ctypes.data_as(ctypes.c_void_p), array.nbytes))
+
+    @staticmethod
+    def unpin(array: np.ndarray):
+        _lib.check(_lib.load().qmb_host_unregister(array.ctypes.data_as(ctypes.c_void_p)))
 
     # -- multi-GPU --------------------------------------------------------------------------
     @staticmethod

@@ -53,17 +53,17 @@ extern "C" int qmb_ctx_create(int device, qmb_ctx_t *out) {
   ctx->sm_count = prop.multiProcessorCount;
   QMB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 4; ++i) QMB_CUDA(cudaEventCreate(&ctx->ev[i]));
-  const char *v = getenv("QMB_NODES_PER_WARP");
-  if (v && atoi(v) == 8) ctx->npw = 8;
+  const char *v = getenv("QMB_VARIANT");
+  if (v && atoi(v) >= 0 && atoi(v) < QMB_N_VARIANTS) ctx->variant = atoi(v);
   *out = ctx;
   return QMB_OK;
 }
 
-extern "C" int qmb_ctx_set_variant(qmb_ctx_t ctx, int nodes_per_warp) {
+extern "C" int qmb_ctx_set_variant(qmb_ctx_t ctx, int variant) {
   if (!ctx) QMB_FAIL(QMB_ERR_ARG, "null context");
-  if (nodes_per_warp == 0) nodes_per_warp = 4;
-  if (nodes_per_warp != 4 && nodes_per_warp != 8) QMB_FAIL(QMB_ERR_ARG, "nodes_per_warp must be 4 or 8");
-  ctx->npw = nodes_per_warp;
+  if (variant < 0) variant = QMB_DEFAULT_VARIANT;
+  if (variant >= QMB_N_VARIANTS) QMB_FAIL(QMB_ERR_ARG, "variant must be in [0, %d)", QMB_N_VARIANTS);
+  ctx->variant = variant;
   return QMB_OK;
 }
 
@@ -80,6 +80,28 @@ extern "C" int qmb_ctx_sync(qmb_ctx_t ctx) {
   return QMB_OK;
 }
 
+extern "C" int qmb_ctx_flush_l2(qmb_ctx_t ctx) {
+  if (!ctx) QMB_FAIL(QMB_ERR_ARG, "null context");
+  QMB_CUDA(cudaSetDevice(ctx->device));
+  const size_t bytes = 256ull << 20;
+  QMB_TRY(ctx->flush.ensure(bytes));
+  QMB_CUDA(cudaMemsetAsync(ctx->flush.p, (int)(ctx->launches & 0xff), bytes, ctx->stream));
+  QMB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return QMB_OK;
+}
+
+extern "C" int qmb_host_register(void *ptr, int64_t bytes) {
+  if (!ptr || bytes <= 0) QMB_FAIL(QMB_ERR_ARG, "bad host range");
+  QMB_CUDA(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+  return QMB_OK;
+}
+
+extern "C" int qmb_host_unregister(void *ptr) {
+  if (!ptr) return QMB_OK;
+  QMB_CUDA(cudaHostUnregister(ptr));
+  return QMB_OK;
+}
+
 extern "C" int qmb_comm_destroy(qmb_ctx_t ctx);
 
 extern "C" int qmb_ctx_destroy(qmb_ctx_t ctx) {
@@ -91,7 +113,7 @@ extern "C" int qmb_ctx_destroy(qmb_ctx_t ctx) {
   ctx->psum.release(); ctx->gm1.release(); ctx->gm2.release(); ctx->gm3.release(); ctx->gi1.release();
   ctx->gi2.release(); ctx->gsum.release(); ctx->ex1.release(); ctx->ex2.release(); ctx->gather.release();
   ctx->r_max.release(); ctx->r_norm.release(); ctx->r_idx.release(); ctx->slow_list.release();
-  ctx->slow_val.release(); ctx->slow_idx.release();
+  ctx->slow_val.release(); ctx->slow_idx.release(); ctx->flush.release();
   for (int i = 0; i < 4; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);

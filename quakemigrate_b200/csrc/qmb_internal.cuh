@@ -37,7 +37,22 @@ void qmb_set_error(const char *fmt, ...);
 // ---------------------------------------------------------------------------------------------
 // geometry constants of the scan kernel
 // ---------------------------------------------------------------------------------------------
-constexpr int QMB_CONSUMER_WARPS = 16;  // node-quads (or octets) processed concurrently per CTA
+// Scan-kernel variants: W consumer warps x NPW nodes per warp form a node tile of tx*ty*tz nodes;
+// every lane carries K time samples, so a time tile is 32*K samples.
+struct QmbVariant {
+  int id, W, NPW, K, tx, ty, tz;
+};
+constexpr int QMB_N_VARIANTS = 7;
+constexpr QmbVariant QMB_VARIANTS[QMB_N_VARIANTS] = {
+    {0, 16, 4, 8, 4, 4, 4},  // 17 warps -> 96 regs/thread
+    {1, 16, 8, 4, 4, 4, 8},
+    {2, 8, 8, 8, 4, 4, 4},   // 9 warps -> 168 regs/thread
+    {3, 8, 8, 4, 4, 4, 4},
+    {4, 12, 4, 8, 4, 4, 3},  // 13 warps -> 128 regs/thread
+    {5, 12, 8, 4, 4, 4, 6},
+    {6, 8, 4, 8, 4, 4, 2},
+};
+constexpr int QMB_DEFAULT_VARIANT = 4;  // measured best on B200 (scripts/sweep_variants.sh)
 constexpr int QMB_CHUNK_ROWS = 16;      // onset rows (station x phase) staged per pipeline stage
 constexpr int QMB_SMEM_BUDGET = 227 * 1024;
 
@@ -72,7 +87,7 @@ struct DevBuf {
 struct qmb_ctx {
   int device = 0;
   int sm_count = 148;
-  int npw = 4;  // nodes per consumer warp: 4 (tile 4x4x4, 256-sample time tiles) or 8 (4x4x8, 128)
+  int variant = QMB_DEFAULT_VARIANT;  // index into QMB_VARIANTS used for tables uploaded next
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t launches = 0;
@@ -96,6 +111,7 @@ struct qmb_ctx {
   DevBuf<int> slow_list;  // [0] = count, [1..] = samples
   DevBuf<double> slow_val;
   DevBuf<unsigned long long> slow_idx;
+  DevBuf<unsigned char> flush;  // L2 eviction scratch (benchmarks)
   int32_t last_n_samples = 0;
   // pinned staging for small D2H
   int *h_pinned = nullptr;
@@ -105,7 +121,7 @@ struct qmb_lut {
   qmb_ctx *ctx = nullptr;
   int32_t nxl = 0, ny = 0, nz = 0, S = 0, Spad = 0;
   int64_t node_offset = 0, n_global = 0, n_local = 0;
-  int npw = 4;       // variant this table was tiled for
+  QmbVariant v = QMB_VARIANTS[QMB_DEFAULT_VARIANT];  // variant this table was tiled for
   int tx = 4, ty = 4, tz = 4, NB = 64;
   int ntx = 0, nty = 0, ntz = 0, n_tiles = 0;
   int32_t max_tau = 0, max_span = 0;

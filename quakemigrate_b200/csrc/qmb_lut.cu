@@ -99,10 +99,10 @@ __global__ void __launch_bounds__(LT_THREADS) k_lut_tile(LutTileParams p) {
 }  // namespace
 
 int qmb_lut_build(qmb_ctx *ctx, qmb_lut *L, const int32_t *d_raw) {
-  L->npw = ctx->npw;
-  L->tx = 4;
-  L->ty = 4;
-  L->tz = (ctx->npw == 8) ? 8 : 4;
+  L->v = QMB_VARIANTS[ctx->variant];
+  L->tx = L->v.tx;
+  L->ty = L->v.ty;
+  L->tz = L->v.tz;
   L->NB = L->tx * L->ty * L->tz;
   L->ntx = (L->nxl + L->tx - 1) / L->tx;
   L->nty = (L->ny + L->ty - 1) / L->ty;

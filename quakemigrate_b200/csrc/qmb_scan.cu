@@ -119,11 +119,9 @@ struct ScanParams {
   double avail;
 };
 
-constexpr int SCAN_THREADS = (QMB_CONSUMER_WARPS + 1) * 32;
-
-template <int NPW, int K, int MODE>
-__global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams p) {
-  constexpr int NB = QMB_CONSUMER_WARPS * NPW;
+template <int W, int NPW, int K, int MODE>
+__global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
+  constexpr int NB = W * NPW;
   constexpr int TT = 32 * K;
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -137,7 +135,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams p) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.n_stages; ++s) {
       mbar_init(bar_base + 8u * s, 1);
-      mbar_init(bar_base + 8u * (p.n_stages + s), QMB_CONSUMER_WARPS);
+      mbar_init(bar_base + 8u * (p.n_stages + s), W);
     }
     fence_mbar_init();
   }
@@ -147,7 +145,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams p) {
   int st = 0;
   uint32_t ph = 0;
 
-  if (warp == QMB_CONSUMER_WARPS) {
+  if (warp == W) {
     // ===================================== producer ==========================================
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const int r = it / p.n_time_tiles, tt = it - r * p.n_time_tiles;
@@ -242,12 +240,18 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams p) {
             off[0] = a & 0xffffu; off[1] = a >> 16; off[2] = b & 0xffffu; off[3] = b >> 16;
             off[4] = cc & 0xffffu; off[5] = cc >> 16; off[6] = d & 0xffffu; off[7] = d >> 16;
           }
+          // issue the whole batch of gathers before the adds: NPW*K independent LDS in flight
+          float v[NPW][K];
 #pragma unroll
           for (int q = 0; q < NPW; ++q) {
             const uint32_t a = row_addr + off[q] * 4u;
 #pragma unroll
-            for (int k = 0; k < K; ++k) acc[q][k] += lds_f32(a + 128u * k);
+            for (int k = 0; k < K; ++k) v[q][k] = lds_f32(a + 128u * k);
           }
+#pragma unroll
+          for (int q = 0; q < NPW; ++q)
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[q][k] += v[q][k];
           row_addr += (uint32_t)p.RS * 4u;
         }
         __syncwarp();
@@ -304,7 +308,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams p) {
 
     if constexpr (MODE == 1) continue;
     // ---- item done: publish this warp's partial reduction -------------------------------------
-    const size_t base = ((size_t)r * QMB_CONSUMER_WARPS + warp) * p.Tpad + (size_t)tt * TT + lane;
+    const size_t base = ((size_t)r * W + warp) * p.Tpad + (size_t)tt * TT + lane;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       const size_t o = base + 32u * k;
@@ -522,13 +526,27 @@ __global__ void k_slow_scatter(const int *slow_list, int n_slow, const double *v
   r_norm[t] = val[b] * n_nodes_global / gsum[t + shift];
 }
 
-template <int NPW, int K, int MODE>
+template <int W, int NPW, int K, int MODE>
 int launch_scan(qmb_ctx *ctx, const ScanParams &p, int grid, size_t smem) {
-  QMB_CUDA(cudaFuncSetAttribute(k_scan<NPW, K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_scan<NPW, K, MODE><<<grid, SCAN_THREADS, smem, ctx->stream>>>(p);
+  QMB_CUDA(cudaFuncSetAttribute(k_scan<W, NPW, K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_scan<W, NPW, K, MODE><<<grid, (W + 1) * 32, smem, ctx->stream>>>(p);
   ctx->launches++;
   QMB_CUDA(cudaGetLastError());
   return QMB_OK;
+}
+
+template <int MODE>
+int dispatch_scan(qmb_ctx *ctx, const QmbVariant &v, const ScanParams &p, int grid, size_t smem) {
+  switch (v.id) {
+    case 0: return launch_scan<16, 4, 8, MODE>(ctx, p, grid, smem);
+    case 1: return launch_scan<16, 8, 4, MODE>(ctx, p, grid, smem);
+    case 2: return launch_scan<8, 8, 8, MODE>(ctx, p, grid, smem);
+    case 3: return launch_scan<8, 8, 4, MODE>(ctx, p, grid, smem);
+    case 4: return launch_scan<12, 4, 8, MODE>(ctx, p, grid, smem);
+    case 5: return launch_scan<12, 8, 4, MODE>(ctx, p, grid, smem);
+    case 6: return launch_scan<8, 4, 8, MODE>(ctx, p, grid, smem);
+  }
+  QMB_FAIL(QMB_ERR_ARG, "unknown kernel variant %d", v.id);
 }
 
 }  // namespace
@@ -539,7 +557,7 @@ int launch_scan(qmb_ctx *ctx, const ScanParams &p, int grid, size_t smem) {
 // Tiling decisions shared by the detect scan and the window pass.
 static int scan_setup(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, long long first, long long T,
                       int32_t available, ScanParams &p, size_t &smem, int &shift_out) {
-  const int NPW = L->npw, K = (NPW == 8) ? 4 : 8, TT = 32 * K, NB = L->NB;
+  const int K = L->v.K, TT = 32 * K, NB = L->NB;
   p.on32 = O->log32.p;
   p.row_stride = O->stride;
   const int shift = (int)((O->front + first) & 3);  // time tiles start `shift` samples early
@@ -608,8 +626,7 @@ int qmb_window_run(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, int32_t fsmp, int32_
   p.coa_map = d_coa_map;
   p.map_accumulate = accumulate;
   if (d_coa_map) QMB_CUDA(cudaMemsetAsync(d_coa_map, 0, (size_t)L->n_local * sizeof(double), ctx->stream));
-  if (L->npw == 8) return launch_scan<8, 4, 1>(ctx, p, ctx->sm_count, smem);
-  return launch_scan<4, 8, 1>(ctx, p, ctx->sm_count, smem);
+  return dispatch_scan<1>(ctx, L->v, p, ctx->sm_count, smem);
 }
 
 int qmb_scan_run(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, int32_t fsmp, int32_t lsmp,
@@ -622,7 +639,7 @@ int qmb_scan_run(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, int32_t fsmp, int32_t 
   QMB_TRY(scan_setup(ctx, L, O, fsmp, T, available, p, smem, shift));
   const int R = p.R, grid = ctx->sm_count;
 
-  const size_t n_part = (size_t)R * QMB_CONSUMER_WARPS * p.Tpad;
+  const size_t n_part = (size_t)R * L->v.W * p.Tpad;
   QMB_TRY(ctx->pm1.ensure(n_part)); QMB_TRY(ctx->pm2.ensure(n_part)); QMB_TRY(ctx->pm3.ensure(n_part));
   QMB_TRY(ctx->pi1.ensure(n_part)); QMB_TRY(ctx->pi2.ensure(n_part)); QMB_TRY(ctx->psum.ensure(n_part));
   p.pm1 = ctx->pm1.p; p.pm2 = ctx->pm2.p; p.pm3 = ctx->pm3.p;
@@ -645,14 +662,13 @@ int qmb_scan_run(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, int32_t fsmp, int32_t 
 
   QMB_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
   int rc;
-  if (L->npw == 8) rc = launch_scan<8, 4, 0>(ctx, p, grid, smem);
-  else rc = launch_scan<4, 8, 0>(ctx, p, grid, smem);
+  rc = dispatch_scan<0>(ctx, L->v, p, grid, smem);
   QMB_TRY(rc);
   QMB_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
 
   // ---- merge partials (local), then across ranks ----------------------------------------------
   const int mb = (int)((p.Tpad + 255) / 256);
-  k_merge<<<mb, 256, 0, ctx->stream>>>(p.pm1, p.pm2, p.pm3, p.pi1, p.pi2, p.psum, R * QMB_CONSUMER_WARPS,
+  k_merge<<<mb, 256, 0, ctx->stream>>>(p.pm1, p.pm2, p.pm3, p.pi1, p.pi2, p.psum, R * L->v.W,
                                        p.Tpad, p.Tpad, p.Tpad, ctx->gm1.p, ctx->gm2.p, ctx->gm3.p, ctx->gi1.p,
                                        ctx->gi2.p, ctx->gsum.p);
   ctx->launches++;

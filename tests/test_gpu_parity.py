@@ -30,10 +30,11 @@ def engine():
     eng.close()
 
 
-@pytest.fixture(scope="module", params=[4, 8])
+@pytest.fixture(scope="module", params=list(range(7)))
 def engine_v(request):
+    """Every kernel tiling variant (QMB_VARIANTS in csrc/qmb_internal.cuh)."""
     from quakemigrate_b200.core import Engine
-    eng = Engine(0, nodes_per_warp=request.param)
+    eng = Engine(0, variant=request.param)
     yield eng
     eng.close()
 
