@@ -1,0 +1,151 @@
+# -*- coding: utf-8 -*-
+"""
+The part of the LUT plugin contract the coalescence hot path consumes, mirrored from
+``quakemigrate/lut/lut.py``:
+
+* ``LUT.serve_traveltimes(sampling_rate, availability)`` (lut.py:502-538): iterate the
+  availability dict in order, stack the float64 ``(nx, ny, nz)`` travel-time grids of the
+  available ``station_phase`` pairs along the last axis, ``rint(tt * sr).astype(int32)``;
+* ``LUT.max_traveltime`` (lut.py:842-845), ``LUT.unit_conversion_factor``;
+* ``Grid3D.index2grid`` / ``index2coord(value, unravel=True)`` (lut.py:142-243): C-order
+  unravel, ``ll_corner + ijk * node_spacing``.  The pyproj inverse projection of the reference
+  is geodesy outside the hot path: pass ``grid2coord`` (callable on an (n, 3) array) to apply
+  one, otherwise coordinates stay in the grid projection.
+
+LUT *construction* (create_lut.py: eikonal solvers, NonLinLoc) is out of scope; tables come from
+the reference's pickles (:func:`read_reference_lut`, needs no pyproj) or from arrays.
+"""
+
+from __future__ import annotations
+
+import pickle
+
+import numpy as np
+
+
+class Grid3D:
+    def __init__(self, node_count, node_spacing, ll_corner, grid2coord=None):
+        self.node_count = np.asarray(node_count, dtype=int)
+        self.node_spacing = np.asarray(node_spacing, dtype=float)
+        self.ll_corner = np.asarray(ll_corner, dtype=float)
+        self.grid2coord = grid2coord
+        self.unit_conversion_factor = 1.0
+
+    def index2grid(self, value, inverse=False, unravel=False):
+        """lut.py:142-180."""
+        if unravel:
+            value = np.column_stack(np.unravel_index(value, self.node_count))
+        else:
+            value = np.array(value)
+        if inverse:
+            out = np.rint((value - self.ll_corner) / self.node_spacing)
+            out = np.vstack(out.astype(int))
+        else:
+            out = np.vstack(self.ll_corner + (value * self.node_spacing))
+        if out.shape[1] == 1:
+            out = out.T
+        return out
+
+    def index2coord(self, value, inverse=False, unravel=False):
+        """lut.py:211-243 with the projection step delegated to ``grid2coord``."""
+        if inverse:
+            raise NotImplementedError("coord -> index needs the forward projection (out of scope)")
+        out = self.index2grid(value, unravel=unravel)
+        return self.grid2coord(out) if self.grid2coord is not None else out
+
+
+class LUT(Grid3D):
+    """Travel-time look-up tables: ``lut[station][phase] -> float64 (nx, ny, nz)`` seconds."""
+
+    def __init__(self, traveltimes: dict, node_count, node_spacing, ll_corner, phases=None,
+                 grid2coord=None):
+        super().__init__(node_count, node_spacing, ll_corner, grid2coord)
+        self.traveltimes = traveltimes
+        self.phases = phases or sorted({p for v in traveltimes.values() for p in v})
+        self.stations = list(traveltimes.keys())
+
+    def __getitem__(self, key):
+        return self.traveltimes[key]
+
+    def serve_traveltimes(self, sampling_rate, availability=None):
+        """lut.py:502-538 (same ordering, same ``TIME_<phase>`` fallback, same rounding)."""
+        if availability is None:
+            traveltimes = self._serve_traveltimes(self.phases)
+        else:
+            traveltimes = []
+            for key, available in availability.items():
+                station, phase = key.split("_")
+                if available == 1:
+                    try:
+                        traveltimes.append(self[station][phase])
+                    except KeyError:
+                        traveltimes.append(self[station][f"TIME_{phase}"])
+            traveltimes = np.stack(traveltimes, axis=-1)
+        return np.rint(traveltimes * sampling_rate).astype(np.int32)
+
+    def _serve_traveltimes(self, phases, stations=None):
+        """lut.py:576-603: phase-outer, station-inner."""
+        stations = self.stations if stations is None else stations
+        traveltimes = []
+        for phase in phases:
+            for station in stations:
+                try:
+                    traveltimes.append(self[station][phase])
+                except KeyError:
+                    traveltimes.append(self[station][f"TIME_{phase}"])
+        return np.stack(traveltimes, axis=-1)
+
+    @property
+    def max_traveltime(self):
+        """lut.py:842-845."""
+        return np.max(self._serve_traveltimes(self.phases))
+
+
+# ------------------------------------------------------------------------------------------------
+# reading the reference's pickled LUTs without pyproj
+# ------------------------------------------------------------------------------------------------
+class _Opaque:
+    """Stand-in for classes we cannot (and need not) import, e.g. pyproj.Proj."""
+
+    def __init__(self, *a, **k):
+        pass
+
+    def __setstate__(self, state):
+        self.__dict__["state"] = state
+
+    def __reduce_ex__(self, protocol):  # pragma: no cover
+        return (_Opaque, ())
+
+
+class _StubUnpickler(pickle.Unpickler):
+    def find_class(self, module, name):
+        root = module.split(".")[0]
+        if root in ("pyproj", "quakemigrate", "matplotlib", "obspy"):
+            return _Opaque
+        return super().find_class(module, name)
+
+
+def read_reference_lut(path, grid2coord=None) -> LUT:
+    """
+    Load a LUT saved by the reference (``LUT.save``: pickle of ``LUT.__dict__``, lut.py:605-620;
+    loader ``quakemigrate/io/core.py:24-51``) without importing pyproj/quakemigrate.
+    """
+    with open(path, "rb") as f:
+        d = _StubUnpickler(f).load()
+    if not isinstance(d, dict):
+        d = getattr(d, "__dict__", {}).get("state", d)
+    tt = d.get("traveltimes", d.get("maps"))
+    node_count = d.get("_node_count", d.get("node_count"))
+    spacing = d.get("node_spacing", d.get("_node_spacing", d.get("cell_size")))
+    ll = d.get("ll_corner", d.get("_ll_corner"))
+    if tt is None or node_count is None:
+        raise ValueError(f"unrecognised LUT pickle (keys: {sorted(d)[:20]})")
+    lut = LUT(tt, node_count, spacing if spacing is not None else np.ones(3),
+              ll if ll is not None else np.zeros(3), phases=d.get("phases"), grid2coord=grid2coord)
+    sd = d.get("station_data")
+    if sd is not None and hasattr(sd, "__getitem__"):
+        try:
+            lut.stations = list(sd["Name"].values)
+        except Exception:
+            pass
+    return lut

@@ -1,0 +1,200 @@
+# -*- coding: utf-8 -*-
+"""
+``QuakeScan._compute`` on the GPU -- the single caller of the coalescence hot path in the
+reference (``quakemigrate/signal/scan.py:594-647``), re-hosted with the same plugin contract:
+
+    onsets, onset_data = self.onset.calculate_onsets(data)                    # scan.py:619
+    traveltimes = self.lut.serve_traveltimes(sampling_rate, availability)     # scan.py:621-623
+    fsmp, lsmp  = time2sample(pre_pad), time2sample(post_pad)                 # scan.py:632-633
+    avail       = sum(availability.values())                                  # scan.py:634
+    map4d       = migrate(onsets, traveltimes, fsmp, lsmp, avail, threads)    # scan.py:635
+    max_coa, max_coa_n, max_idx = find_max_coa(map4d, threads)                # scan.py:638
+    coord       = self.lut.index2coord(max_idx, unravel=True)                 # scan.py:639
+
+Differences, all behind the same return values:
+
+* migrate + find_max_coa are one fused device pass; ``map4d`` never exists in detect;
+* the int32 travel-time stack is uploaded once per availability pattern and cached on the device
+  (the reference rebuilds it every call, lut.py:502-538);
+* locate does not return the full ``(nx, ny, nz, T)`` volume: it returns the marginal window the
+  reference would cut out of it (``Event.trim2window``, io/event.py:421-439) and its time-sum
+  (``coa_map``, scan.py:720) -- use :meth:`QuakeScan.compute_locate`.  The reference-shaped
+  ``_compute(data, event)`` that materialises the whole volume is kept for small problems.
+
+``onset`` may be any :class:`quakemigrate_b200.onsets.Onset` (or duck-typed equivalent returning
+host arrays); if its ``OnsetData`` carries ``device_onsets`` the host->device copy is skipped.
+"""
+
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+
+from .core import DeviceOnsets, Engine
+from .onsets import Onset
+from .synthetic import time2sample
+
+
+class LUTPhasesException(Exception):
+    """quakemigrate/util.py LUTPhasesException (raised at scan.py:624-629)."""
+
+
+def marginal_window_indices(max_coa: np.ndarray, marginal_window: float, sampling_rate: int):
+    """
+    Sample range the reference keeps for the marginalised map.
+
+    ``Event.add_compute_output`` sets ``otime`` to the time of the maximum of COA
+    (io/event.py:239-240, first maximum); ``Event.trim2window`` keeps rows with
+    ``otime - mw <= DT <= otime + mw`` and slices ``map4d[..., idx[0]:idx[-1]]`` -- END-EXCLUSIVE,
+    i.e. the last kept row is dropped from the map (io/event.py:427-435).
+    Returns ``(i0, i1, imax)`` with the map window ``[i0, i1)``.
+    """
+    imax = int(np.argmax(max_coa))
+    half = int(round(marginal_window * sampling_rate))
+    first = max(0, imax - half)
+    last = min(len(max_coa) - 1, imax + half)
+    return first, last, imax
+
+
+class QuakeScan:
+    """
+    GPU re-host of the compute core of ``quakemigrate.signal.scan.QuakeScan``.
+
+    Parameters mirror the reference constructor where they touch the hot path (scan.py:204-280):
+    ``lut``, ``onset``, and the attributes ``marginal_window``, ``timestep``, ``threads``
+    (accepted, ignored).  Archive reading, output writing, picking and magnitudes are out of
+    scope; callers hand in pre-processed waveform containers.
+    """
+
+    def __init__(self, lut, onset, engine: Engine | None = None, **kwargs):
+        if not isinstance(onset, Onset) and not hasattr(onset, "calculate_onsets"):
+            raise TypeError("onset must implement the Onset plugin interface")  # scan.py:209-212
+        self.lut = lut
+        self.onset = onset
+        self.onset.post_pad = lut.max_traveltime  # scan.py:213
+        self.engine = engine or getattr(onset, "engine", None) or Engine(0)
+        if getattr(onset, "engine", "absent") is None:
+            onset.engine = self.engine
+        self.marginal_window = kwargs.get("marginal_window", 2.0)
+        self.timestep = kwargs.get("timestep", 120.0)
+        self.threads = kwargs.get("threads", 1)
+        self.scan_rate = kwargs.get("scan_rate", self.onset.sampling_rate)
+        self.pre_pad = self.post_pad = 0.0
+        self._lut_cache: dict = {}
+
+    # -- travel-time cache -----------------------------------------------------------------------
+    def _device_lut(self, sampling_rate, availability):
+        key = (int(sampling_rate), tuple(availability.items()))
+        if key not in self._lut_cache:
+            try:
+                traveltimes = self.lut.serve_traveltimes(sampling_rate, availability)
+            except KeyError as e:
+                raise LUTPhasesException(
+                    f"Attempting to migrate phases; but traveltimes for {e} not found in the LUT."
+                )
+            if len(self._lut_cache) >= 4:  # bound device memory: drop the oldest pattern
+                old = next(iter(self._lut_cache))
+                self._lut_cache.pop(old).free()
+            self._lut_cache[key] = self.engine.upload_lut(traveltimes)
+        return self._lut_cache[key]
+
+    def set_pads(self, timespan: float):
+        """``pre_pad, post_pad = onset.pad(timespan)`` (scan.py:425 detect, :494 locate)."""
+        self.pre_pad, self.post_pad = self.onset.pad(timespan)
+        return self.pre_pad, self.post_pad
+
+    # -- the hot path ------------------------------------------------------------------------------
+    def _prepare(self, data):
+        onsets, onset_data = self.onset.calculate_onsets(data)
+        dlut = self._device_lut(onset_data.sampling_rate, onset_data.availability)
+        fsmp = time2sample(self.pre_pad, onset_data.sampling_rate)
+        lsmp = time2sample(self.post_pad, onset_data.sampling_rate)
+        avail = int(np.sum([value for _, value in onset_data.availability.items()]))
+        dev = getattr(onset_data, "device_onsets", None)
+        owned = False
+        if not isinstance(dev, DeviceOnsets):
+            n_onsets, t_samples = np.shape(onsets)
+            if n_onsets != dlut.n_rows:  # lib.py:105-108
+                raise ValueError(
+                    f"Mismatch between number of stations for data and LUT, {n_onsets}:{dlut.n_rows}"
+                )
+            dev, owned = self.engine.upload_onsets(onsets), True
+        return onsets, onset_data, dlut, dev, owned, fsmp, lsmp, avail
+
+    def _compute(self, data, event=None):
+        """
+        Reference-shaped entry (scan.py:594-647).  Detect (``event is None``):
+        ``(time, max_coa, max_coa_n, coord, onset_data)``.  Locate: additionally the FULL
+        ``map4d`` (materialised through the marginal-window kernel over the whole span; large).
+        """
+        onsets, onset_data, dlut, dev, owned, fsmp, lsmp, avail = self._prepare(data)
+        n_samples = dev.n_total - fsmp - lsmp
+        if n_samples <= 0:  # lib.py:109-110
+            raise ValueError("Data array smaller than coalescence array.")
+        self.engine.detect_device(dlut, dev, fsmp, lsmp, avail)
+        max_coa, max_coa_n, max_idx = self.engine.detect_fetch(n_samples)
+        coord = self.lut.index2coord(max_idx, unravel=True)
+        try:
+            if event is None:
+                time = data.starttime + self.pre_pad
+                return time, max_coa, max_coa_n, coord, onset_data
+            _, map4d = self.engine.locate_window(dlut, dev, fsmp, lsmp, avail, 0, n_samples,
+                                                 return_map4d=True)
+            times = data.starttime + self.pre_pad + np.arange(n_samples) / onset_data.sampling_rate
+            return times, max_coa, max_coa_n, coord, map4d, onset_data
+        finally:
+            if owned:
+                dev.free()
+
+    def compute_locate(self, data, marginal_window: float | None = None, return_map4d: bool = False):
+        """
+        Fast locate: the max-coalescence traces over the whole span, then only the marginal
+        window around the peak (io/event.py:421-439) is re-migrated on the device.
+
+        Returns a dict with ``times``, ``max_coa``, ``max_coa_n``, ``coord``, ``window`` =
+        ``(i0, i1)``, ``coa_map`` = ``sum_t map4d[..., i0:i1]`` (scan.py:720; divide by its
+        ``nanmax`` for the normalised map of scan.py:721), optionally ``map4d`` (the window slab),
+        and ``onset_data``.
+        """
+        mw = self.marginal_window if marginal_window is None else marginal_window
+        onsets, onset_data, dlut, dev, owned, fsmp, lsmp, avail = self._prepare(data)
+        try:
+            n_samples = dev.n_total - fsmp - lsmp
+            if n_samples <= 0:
+                raise ValueError("Data array smaller than coalescence array.")
+            self.engine.detect_device(dlut, dev, fsmp, lsmp, avail)
+            max_coa, max_coa_n, max_idx = self.engine.detect_fetch(n_samples)
+            i0, i1, imax = marginal_window_indices(max_coa, mw, onset_data.sampling_rate)
+            out = {
+                "times": data.starttime + self.pre_pad + np.arange(n_samples) / onset_data.sampling_rate,
+                "max_coa": max_coa, "max_coa_n": max_coa_n,
+                "coord": self.lut.index2coord(max_idx, unravel=True),
+                "window": (i0, i1), "peak_sample": imax, "onset_data": onset_data,
+            }
+            if i1 > i0:
+                res = self.engine.locate_window(dlut, dev, fsmp, lsmp, avail, i0, i1, return_map4d=return_map4d)
+                out["coa_map"], out["map4d"] = (res if return_map4d else (res, None))
+            else:  # degenerate single-row window: the reference slices an empty map
+                out["coa_map"] = np.zeros(dlut.shape[:-1])
+                out["map4d"] = np.zeros(dlut.shape[:-1] + (0,)) if return_map4d else None
+            return out
+        finally:
+            if owned:
+                dev.free()
+
+    def detect_chunks(self, chunks):
+        """
+        The loop of ``_continuous_compute`` (scan.py:434-462) over already-read waveform chunks:
+        yields ``(time, max_coa, max_coa_n, coord)`` per chunk.  Chunks must have been read with
+        ``pre_pad`` / ``post_pad`` from :meth:`set_pads` so that they are independent.
+        """
+        for i, data in enumerate(chunks):
+            logging.debug("detect chunk %d", i)
+            time, max_coa, max_coa_n, coord, _ = self._compute(data)
+            yield time, max_coa, max_coa_n, coord
+
+    def close(self):
+        for dlut in self._lut_cache.values():
+            dlut.free()
+        self._lut_cache.clear()

@@ -1,0 +1,103 @@
+# -*- coding: utf-8 -*-
+"""
+Plugin-level parity: quakemigrate_b200.scan.QuakeScan._compute (GPU) against a line-by-line CPU
+restatement of the reference's QuakeScan._compute (scan.py:618-647) built from the oracle.
+"""
+
+import numpy as np
+import pytest
+
+from oracle import qm_oracle as O
+from quakemigrate_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem():
+    cfg = syn.CONFIGS["cfg2"].scaled(grid=(14, 12, 9), n_samples=1200, n_rows=8, name="api")
+    prob = syn.make_problem(cfg)
+    n_sta = len(prob.stations_xyz)
+    h = cfg.node_spacing_km
+    from quakemigrate_b200.lut import LUT
+    from quakemigrate_b200.onsets import WaveformData
+    nx, ny, nz = cfg.grid
+    gx, gy, gz = np.meshgrid(np.arange(nx) * h, np.arange(ny) * h, np.arange(nz) * h, indexing="ij")
+    tts = {}
+    for k in range(n_sta):
+        d = np.sqrt((gx - prob.stations_xyz[k, 0]) ** 2 + (gy - prob.stations_xyz[k, 1]) ** 2 + gz ** 2)
+        tts[f"ST{k:03d}"] = {"P": d / cfg.vp, "S": d / cfg.vs}
+    lut = LUT(tts, cfg.grid, (h, h, h), (0.0, 0.0, 0.0))
+    channels = {f"ST{k:03d}": {"Z": prob.waveforms[3 * k], "N": prob.waveforms[3 * k + 1],
+                               "E": prob.waveforms[3 * k + 2]} for k in range(n_sta)}
+    # one station lost its horizontals: exercises availability + LUT re-serving
+    del channels["ST002"]["N"], channels["ST002"]["E"]
+    data = WaveformData(channels, starttime=1000.0, sampling_rate=cfg.sampling_rate)
+    return cfg, prob, lut, data
+
+
+def _reference_compute(cfg, lut, data, pre_pad, post_pad, position):
+    """scan.py:618-639 with the reference's own building blocks (oracle back-ends)."""
+    sr = cfg.sampling_rate
+    nsta, nlta = syn.time2sample(cfg.sta, sr) + 1, syn.time2sample(cfg.lta, sr) + 1
+    fn = O.overlapping_sta_lta if position == "classic" else O.centred_sta_lta
+    onsets, availability = [], {}
+    for phase, comps in (("P", "Z"), ("S", "NE")):
+        for st in data.stations:
+            have = [c for c in comps if c in data.channels[st]]
+            availability[f"{st}_{phase}"] = 1 if have else 0
+            if not have:
+                continue
+            ons = np.array([fn(data.channels[st][c] ** 2, nsta, nlta) for c in have])
+            onset = np.sqrt(np.sum([o ** 2 for o in ons], axis=0) / len(ons))
+            onsets.append(np.clip(onset, 0.4, np.inf))
+    onsets = np.stack(onsets, axis=0)
+    traveltimes = lut.serve_traveltimes(sr, availability)
+    fsmp, lsmp = syn.time2sample(pre_pad, sr), syn.time2sample(post_pad, sr)
+    avail = int(np.sum(list(availability.values())))
+    map4d = O.migrate(onsets, traveltimes, fsmp, lsmp, avail, threads=4)
+    max_coa, max_coa_n, max_idx = O.find_max_coa(map4d, threads=4)
+    return onsets, availability, map4d, max_coa, max_coa_n, max_idx, lut.index2coord(max_idx, unravel=True)
+
+
+@pytest.mark.parametrize("position", ["classic", "centred"])
+def test_compute_detect_and_locate(position):
+    from quakemigrate_b200.core import Engine
+    from quakemigrate_b200.onsets import STALTAOnset
+    from quakemigrate_b200.scan import QuakeScan, marginal_window_indices
+
+    cfg, prob, lut, data = _problem()
+    eng = Engine(0)
+    onset = STALTAOnset(engine=eng, sampling_rate=cfg.sampling_rate, position=position,
+                        sta_lta_windows={"P": [cfg.sta, cfg.lta], "S": [cfg.sta, cfg.lta]})
+    scan = QuakeScan(lut, onset, engine=eng, marginal_window=1.0)
+    # pads exactly as the synthetic problem was built (onset.pad on the scan timespan)
+    pre_pad, post_pad = scan.set_pads(cfg.n_samples / cfg.sampling_rate)
+    assert (syn.time2sample(pre_pad, 100), syn.time2sample(post_pad, 100)) == (prob.fsmp, prob.lsmp)
+
+    ref = _reference_compute(cfg, lut, data, pre_pad, post_pad, position)
+    r_onsets, r_avail, r_map4d, r_max, r_norm, r_idx, r_coord = ref
+
+    time, max_coa, max_coa_n, coord, onset_data = scan._compute(data)
+    assert time == data.starttime + pre_pad
+    assert list(onset_data.availability.items()) == list(r_avail.items())
+    assert np.array_equal(np.argmax(r_map4d.reshape(-1, r_map4d.shape[-1]), axis=0), r_idx)
+    np.testing.assert_allclose(max_coa, r_max, rtol=1e-8)
+    np.testing.assert_allclose(max_coa_n, r_norm, rtol=2e-6)
+    np.testing.assert_allclose(coord, r_coord, rtol=0, atol=0)      # identical arg-max -> identical coords
+
+    # reference-shaped locate: the whole volume
+    times, mc, mcn, crd, map4d, _ = scan._compute(data, event=object())
+    assert map4d.shape == r_map4d.shape
+    np.testing.assert_allclose(map4d, r_map4d, rtol=1e-5)
+
+    # fast locate: marginal window only (event.py:421-439, scan.py:720-721)
+    out = scan.compute_locate(data, return_map4d=True)
+    i0, i1, imax = marginal_window_indices(r_max, 1.0, cfg.sampling_rate)
+    assert out["window"] == (i0, i1) and out["peak_sample"] == imax
+    want = r_map4d[..., i0:i1]
+    np.testing.assert_allclose(out["map4d"], want, rtol=1e-5)
+    coa_map = out["coa_map"] / np.nanmax(out["coa_map"])
+    r_coa_map = want.sum(axis=-1)
+    np.testing.assert_allclose(coa_map, r_coa_map / np.nanmax(r_coa_map), rtol=1e-5)
+    scan.close()
+    eng.close()
