@@ -113,7 +113,12 @@ extern "C" int qmb_ctx_destroy(qmb_ctx_t ctx) {
   ctx->psum.release(); ctx->gm1.release(); ctx->gm2.release(); ctx->gm3.release(); ctx->gi1.release();
   ctx->gi2.release(); ctx->gsum.release(); ctx->ex1.release(); ctx->ex2.release(); ctx->gather.release();
   ctx->r_max.release(); ctx->r_norm.release(); ctx->r_idx.release(); ctx->slow_list.release();
-  ctx->slow_val.release(); ctx->slow_idx.release(); ctx->flush.release();
+  ctx->slow_val.release(); ctx->slow_idx.release(); ctx->flush.release(); ctx->stage_lin.release();
+  if (ctx->tmp_onsets) {
+    ctx->tmp_onsets->log32.release(); ctx->tmp_onsets->log64.release(); ctx->tmp_onsets->rowmax.release();
+    delete ctx->tmp_onsets;
+    ctx->tmp_onsets = nullptr;
+  }
   for (int i = 0; i < 4; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -238,6 +243,7 @@ extern "C" int qmb_lut_upload(qmb_ctx_t ctx, const int32_t *lut, int32_t nx_loca
   QMB_CUDA(cudaSetDevice(ctx->device));
   qmb_lut *L = new qmb_lut();
   L->ctx = ctx;
+  L->device = ctx->device;
   L->nxl = nx_local; L->ny = ny; L->nz = nz; L->S = n_rows;
   L->node_offset = node_offset; L->n_global = n_nodes_global; L->n_local = n_local;
   int32_t *d_raw = nullptr;
@@ -266,7 +272,7 @@ extern "C" int qmb_lut_upload(qmb_ctx_t ctx, const int32_t *lut, int32_t nx_loca
 
 extern "C" int qmb_lut_free(qmb_lut_t L) {
   if (!L) return QMB_OK;
-  if (L->ctx) cudaSetDevice(L->ctx->device);
+  cudaSetDevice(L->device);
   L->tau16.release(); L->tmin.release(); L->span.release(); L->nodeidx.release();
   delete L;
   return QMB_OK;
@@ -286,9 +292,21 @@ extern "C" int qmb_lut_info(qmb_lut_t L, qmb_lut_info_t *info) {
 // ---------------------------------------------------------------------------------------------
 extern "C" int qmb_onsets_free(qmb_onsets_t O) {
   if (!O) return QMB_OK;
-  if (O->ctx) cudaSetDevice(O->ctx->device);
+  cudaSetDevice(O->device);
   O->log32.release(); O->log64.release(); O->rowmax.release();
   delete O;
+  return QMB_OK;
+}
+
+// H2D through the context's reusable staging buffer, then clip/log into O's (reusable) rows.
+static int onsets_fill(qmb_ctx *ctx, qmb_onsets *O, const double *onsets, int32_t n_rows, int64_t n_total) {
+  const size_t count = (size_t)n_rows * n_total;
+  QMB_TRY(ctx->stage_lin.ensure(count));
+  O->S = n_rows;
+  O->P = n_total;
+  QMB_CUDA(cudaMemcpyAsync(ctx->stage_lin.p, onsets, count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  QMB_TRY(qmb_onsets_prepare(ctx, O, ctx->stage_lin.p, 0));
+  QMB_CUDA(cudaStreamSynchronize(ctx->stream));  // the staging buffer may be reused right away
   return QMB_OK;
 }
 
@@ -298,20 +316,10 @@ extern "C" int qmb_onsets_upload(qmb_ctx_t ctx, const double *onsets, int32_t n_
   *out = nullptr;
   if (n_rows <= 0 || n_total <= 0) QMB_FAIL(QMB_ERR_ARG, "empty onset array");
   QMB_CUDA(cudaSetDevice(ctx->device));
-  double *d_lin = nullptr;
-  const size_t bytes = (size_t)n_rows * n_total * sizeof(double);
-  QMB_CUDA(cudaMalloc((void **)&d_lin, bytes));
   qmb_onsets *O = new qmb_onsets();
-  O->ctx = ctx; O->S = n_rows; O->P = n_total;
-  int rc = QMB_OK;
-  cudaError_t e = cudaMemcpyAsync(d_lin, onsets, bytes, cudaMemcpyHostToDevice, ctx->stream);
-  if (e != cudaSuccess) {
-    qmb_set_error("H2D of the onset functions: %s", cudaGetErrorString(e));
-    rc = QMB_ERR_CUDA;
-  }
-  if (rc == QMB_OK) rc = qmb_onsets_prepare(ctx, O, d_lin, 0);
-  cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_lin);
+  O->ctx = ctx;
+  O->device = ctx->device;
+  int rc = onsets_fill(ctx, O, onsets, n_rows, n_total);
   if (rc != QMB_OK) {
     qmb_onsets_free(O);
     return rc;
@@ -352,7 +360,7 @@ extern "C" int qmb_onsets_from_waveforms(qmb_ctx_t ctx, const double *waveforms,
   const size_t pair_elems = (size_t)n_pairs * n_total;
   int rc = QMB_OK;
   qmb_onsets *O = new qmb_onsets();
-  O->ctx = ctx; O->S = n_rows; O->P = n_total;
+  O->ctx = ctx; O->device = ctx->device; O->S = n_rows; O->P = n_total;
   auto cleanup = [&]() {
     cudaStreamSynchronize(ctx->stream);
     if (d_wf) cudaFree(d_wf);
@@ -455,12 +463,16 @@ extern "C" int qmb_detect(qmb_ctx_t ctx, qmb_lut_t lut, const double *onsets, in
   if (!ctx || !lut) QMB_FAIL(QMB_ERR_ARG, "null argument");
   if (n_rows != lut->S)
     QMB_FAIL(QMB_ERR_ARG, "Mismatch between number of stations for data and LUT, %d:%d", n_rows, lut->S);
-  qmb_onsets_t O = nullptr;
-  QMB_TRY(qmb_onsets_upload(ctx, onsets, n_rows, n_total, &O));
-  int rc = qmb_detect_device(ctx, lut, O, fsmp, lsmp, available, nullptr);
-  if (rc == QMB_OK) rc = qmb_detect_fetch(ctx, max_coa, max_norm_coa, max_coa_idx, (int32_t)(n_total - fsmp - lsmp));
-  qmb_onsets_free(O);
-  return rc;
+  if (!onsets || n_total <= 0) QMB_FAIL(QMB_ERR_ARG, "empty onset array");
+  QMB_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->tmp_onsets) {
+    ctx->tmp_onsets = new qmb_onsets();
+    ctx->tmp_onsets->ctx = ctx;
+    ctx->tmp_onsets->device = ctx->device;
+  }
+  QMB_TRY(onsets_fill(ctx, ctx->tmp_onsets, onsets, n_rows, n_total));
+  QMB_TRY(qmb_detect_device(ctx, lut, ctx->tmp_onsets, fsmp, lsmp, available, nullptr));
+  return qmb_detect_fetch(ctx, max_coa, max_norm_coa, max_coa_idx, (int32_t)(n_total - fsmp - lsmp));
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -112,6 +112,8 @@ struct qmb_ctx {
   DevBuf<double> slow_val;
   DevBuf<unsigned long long> slow_idx;
   DevBuf<unsigned char> flush;  // L2 eviction scratch (benchmarks)
+  DevBuf<double> stage_lin;     // H2D staging of linear onsets (reused across calls)
+  struct qmb_onsets *tmp_onsets = nullptr;  // onset rows of the one-call qmb_detect (reused)
   int32_t last_n_samples = 0;
   // pinned staging for small D2H
   int *h_pinned = nullptr;
@@ -119,6 +121,7 @@ struct qmb_ctx {
 
 struct qmb_lut {
   qmb_ctx *ctx = nullptr;
+  int device = 0;  // copied from ctx: handles may outlive their context
   int32_t nxl = 0, ny = 0, nz = 0, S = 0, Spad = 0;
   int64_t node_offset = 0, n_global = 0, n_local = 0;
   QmbVariant v = QMB_VARIANTS[QMB_DEFAULT_VARIANT];  // variant this table was tiled for
@@ -133,6 +136,7 @@ struct qmb_lut {
 
 struct qmb_onsets {
   qmb_ctx *ctx = nullptr;
+  int device = 0;
   int32_t S = 0;
   int64_t P = 0;          // samples per row as seen by the caller (fsmp + T + lsmp)
   int64_t stride = 0;     // device row stride in elements (multiple of 4)

@@ -94,7 +94,7 @@ extern "C" void migrate(double *onsets, int32_t *lookup_tables, double *map4d, i
 
   // onsets: upload once, skip the clip/log
   qmb_onsets *O = new qmb_onsets();
-  O->ctx = ctx; O->S = n_stations; O->P = P;
+  O->ctx = ctx; O->device = ctx->device; O->S = n_stations; O->P = P;
   double *d_lin = nullptr;
   const size_t on_bytes = (size_t)n_stations * P * sizeof(double);
   if (cudaMalloc((void **)&d_lin, on_bytes) != cudaSuccess) die("cudaMalloc(onsets)");
@@ -116,6 +116,7 @@ extern "C" void migrate(double *onsets, int32_t *lookup_tables, double *map4d, i
     // pseudo-grid (ceil(nn/16), 4, 4): 64 consecutive flat nodes form one tile
     qmb_lut *L = new qmb_lut();
     L->ctx = ctx;
+    L->device = ctx->device;
     L->nxl = (int32_t)((nn + 15) / 16); L->ny = 4; L->nz = 4; L->S = n_stations;
     L->node_offset = 0; L->n_global = nn; L->n_local = nn;
     int32_t *d_raw = nullptr;
