@@ -274,6 +274,7 @@ extern "C" int qmb_lut_free(qmb_lut_t L) {
   if (!L) return QMB_OK;
   cudaSetDevice(L->device);
   L->tau16.release(); L->tmin.release(); L->span.release(); L->nodeidx.release();
+  L->boxes.release(); L->slotmap.release();
   delete L;
   return QMB_OK;
 }
@@ -283,7 +284,8 @@ extern "C" int qmb_lut_info(qmb_lut_t L, qmb_lut_info_t *info) {
   info->n_nodes_local = L->n_local; info->n_nodes_global = L->n_global; info->node_offset = L->node_offset;
   info->n_rows = L->S; info->max_tau = L->max_tau; info->max_tile_span = L->max_span;
   info->n_tiles = L->n_tiles; info->nodes_per_tile = L->NB;
-  info->device_bytes = (int64_t)(L->tau16.bytes() + L->tmin.bytes() + L->span.bytes() + L->nodeidx.bytes());
+  info->device_bytes = (int64_t)(L->tau16.bytes() + L->tmin.bytes() + L->span.bytes() + L->nodeidx.bytes() +
+                                  L->boxes.bytes() + L->slotmap.bytes());
   return QMB_OK;
 }
 

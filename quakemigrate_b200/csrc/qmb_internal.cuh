@@ -132,6 +132,8 @@ struct qmb_lut {
   DevBuf<int32_t> tmin;     // [n_tiles][Spad]       multiple of 4
   DevBuf<uint16_t> span;    // [n_tiles][Spad]       max(tau16) within the tile
   DevBuf<uint32_t> nodeidx; // [n_tiles][NB]         global flat node index or 0xFFFFFFFF (pad)
+  DevBuf<int> boxes;        // [n_tiles][9]          tile origin, shape, region end
+  DevBuf<uint32_t> slotmap; // [n_local]             tile * NB + slot of each local node
 };
 
 struct qmb_onsets {

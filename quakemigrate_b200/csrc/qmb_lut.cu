@@ -20,8 +20,9 @@ constexpr int LT_ROWS = 32;  // rows handled per pass through shared memory
 struct LutTileParams {
   const int32_t *raw;  // (nxl*ny*nz, S)
   int nxl, ny, nz, S, Spad;
-  int tx, ty, tz, NB;
-  int ntx, nty, ntz;
+  int NB;
+  const int *boxes;    // [n_tiles][9]: origin x0,y0,z0; tile shape sx,sy,sz; region end x1,y1,z1
+  uint32_t *slotmap;   // [n_local]: tile * NB + slot of every node
   long long node_offset, n_valid;
   uint16_t *tau16;
   int32_t *tmin;
@@ -34,21 +35,25 @@ __global__ void __launch_bounds__(LT_THREADS) k_lut_tile(LutTileParams p) {
   __shared__ int s_tau[LT_ROWS][128 + 1];
   __shared__ long long s_node[128];  // clamped local flat index per slot
   const int j = blockIdx.x;
-  const int tzi = j % p.ntz, tyi = (j / p.ntz) % p.nty, txi = j / (p.ntz * p.nty);
+  const int *bx = p.boxes + (size_t)j * 9;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NWARPS = LT_THREADS / 32;
 
   if (tid < p.NB) {
-    const int dz = tid % p.tz, dy = (tid / p.tz) % p.ty, dx = tid / (p.tz * p.ty);
-    const int ix = txi * p.tx + dx, iy = tyi * p.ty + dy, iz = tzi * p.tz + dz;
-    const int cx = min(ix, p.nxl - 1), cy = min(iy, p.ny - 1), cz = min(iz, p.nz - 1);
+    const int sx = bx[3], sy = bx[4], sz = bx[5];
+    (void)sx;
+    const int dz = tid % sz, dy = (tid / sz) % sy, dx = tid / (sz * sy);
+    const int ix = bx[0] + dx, iy = bx[1] + dy, iz = bx[2] + dz;
+    // slots outside the tile's region (or the grid) are padding; they replicate the nearest
+    // in-region node so that they do not widen the tile's travel-time range
+    const int cx = min(ix, bx[6] - 1), cy = min(iy, bx[7] - 1), cz = min(iz, bx[8] - 1);
     long long local = ((long long)cx * p.ny + cy) * p.nz + cz;
     const long long flat = ((long long)ix * p.ny + iy) * p.nz + iz;
-    const bool valid = ix < p.nxl && iy < p.ny && iz < p.nz && flat < p.n_valid;
+    const bool valid = ix < bx[6] && iy < bx[7] && iz < bx[8] && flat < p.n_valid;
     if (local >= p.n_valid) local = p.n_valid - 1;  // ragged last x-plane of a pseudo-grid
     s_node[tid] = local;
-    p.nodeidx[(size_t)j * p.NB + tid] =
-        valid ? (uint32_t)(p.node_offset + ((long long)ix * p.ny + iy) * p.nz + iz) : 0xFFFFFFFFu;
+    p.nodeidx[(size_t)j * p.NB + tid] = valid ? (uint32_t)(p.node_offset + flat) : 0xFFFFFFFFu;
+    if (valid) p.slotmap[flat] = (uint32_t)j * (uint32_t)p.NB + (uint32_t)tid;
   }
   __syncthreads();
 
@@ -98,18 +103,74 @@ __global__ void __launch_bounds__(LT_THREADS) k_lut_tile(LutTileParams p) {
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------
+// host: cover the slab with node tiles.  The bulk uses the variant's preferred shape; what does
+// not divide evenly is covered by up to three remainder slabs, each tiled with the factorisation
+// of NB that wastes the fewest slots (ties: most compact), so padding stays ~0.2 % instead of the
+// ~6 % a single padded shape costs on e.g. a 101x101x51 grid.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct Region {
+  int x0, y0, z0, x1, y1, z1;
+};
+
+void best_shape(int NB, int bx, int by, int bz, int &sx, int &sy, int &sz) {
+  long long best_vol = -1;
+  int best_sum = 0;
+  for (int a = 1; a <= NB; ++a) {
+    if (NB % a) continue;
+    for (int b = 1; b <= NB / a; ++b) {
+      if ((NB / a) % b) continue;
+      const int c = NB / a / b;
+      const long long vol = (long long)((bx + a - 1) / a) * a * ((by + b - 1) / b) * b * ((bz + c - 1) / c) * c;
+      const int sum = a + b + c;
+      if (best_vol < 0 || vol < best_vol || (vol == best_vol && sum < best_sum)) {
+        best_vol = vol; best_sum = sum; sx = a; sy = b; sz = c;
+      }
+    }
+  }
+}
+
+void tile_region(const Region &r, int sx, int sy, int sz, std::vector<int> &boxes) {
+  for (int x = r.x0; x < r.x1; x += sx)
+    for (int y = r.y0; y < r.y1; y += sy)
+      for (int z = r.z0; z < r.z1; z += sz) {
+        const int b[9] = {x, y, z, sx, sy, sz, r.x1, r.y1, r.z1};
+        boxes.insert(boxes.end(), b, b + 9);
+      }
+}
+
+}  // namespace
+
 int qmb_lut_build(qmb_ctx *ctx, qmb_lut *L, const int32_t *d_raw) {
   L->v = QMB_VARIANTS[ctx->variant];
   L->tx = L->v.tx;
   L->ty = L->v.ty;
   L->tz = L->v.tz;
   L->NB = L->tx * L->ty * L->tz;
-  L->ntx = (L->nxl + L->tx - 1) / L->tx;
-  L->nty = (L->ny + L->ty - 1) / L->ty;
-  L->ntz = (L->nz + L->tz - 1) / L->tz;
-  const long long nt = (long long)L->ntx * L->nty * L->ntz;
-  if (nt > 0x7fffffffLL) QMB_FAIL(QMB_ERR_UNSUPPORTED, "too many node tiles (%lld)", nt);
+  std::vector<int> boxes;
+  {
+    const int Mx = (L->nxl / L->tx) * L->tx, My = (L->ny / L->ty) * L->ty, Mz = (L->nz / L->tz) * L->tz;
+    int sx, sy, sz;
+    if (Mx > 0 && My > 0 && Mz > 0) tile_region({0, 0, 0, Mx, My, Mz}, L->tx, L->ty, L->tz, boxes);
+    const Region rem[3] = {
+        {Mx, 0, 0, L->nxl, L->ny, L->nz},                       // x remainder (everything if Mx == 0)
+        {0, My, 0, Mx, L->ny, L->nz},                           // y remainder
+        {0, 0, (My > 0 ? Mz : 0), Mx, My, L->nz},               // z remainder
+    };
+    for (const Region &r : rem) {
+      if (r.x1 <= r.x0 || r.y1 <= r.y0 || r.z1 <= r.z0) continue;
+      best_shape(L->NB, r.x1 - r.x0, r.y1 - r.y0, r.z1 - r.z0, sx, sy, sz);
+      tile_region(r, sx, sy, sz, boxes);
+    }
+  }
+  const long long nt = (long long)(boxes.size() / 9);
+  if (nt > 0x7fffffffLL / 128) QMB_FAIL(QMB_ERR_UNSUPPORTED, "too many node tiles (%lld)", nt);
   L->n_tiles = (int)nt;
+  QMB_TRY(L->boxes.ensure(boxes.size()));
+  QMB_TRY(L->slotmap.ensure((size_t)L->n_local));
+  QMB_CUDA(cudaMemcpyAsync(L->boxes.p, boxes.data(), boxes.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   L->Spad = ((L->S + QMB_CHUNK_ROWS - 1) / QMB_CHUNK_ROWS) * QMB_CHUNK_ROWS;
 
   QMB_TRY(L->tau16.ensure((size_t)L->n_tiles * L->Spad * L->NB));
@@ -124,8 +185,9 @@ int qmb_lut_build(qmb_ctx *ctx, qmb_lut *L, const int32_t *d_raw) {
   LutTileParams p;
   p.raw = d_raw;
   p.nxl = L->nxl; p.ny = L->ny; p.nz = L->nz; p.S = L->S; p.Spad = L->Spad;
-  p.tx = L->tx; p.ty = L->ty; p.tz = L->tz; p.NB = L->NB;
-  p.ntx = L->ntx; p.nty = L->nty; p.ntz = L->ntz;
+  p.NB = L->NB;
+  p.boxes = L->boxes.p;
+  p.slotmap = L->slotmap.p;
   p.node_offset = L->node_offset;
   p.n_valid = L->n_local;
   p.tau16 = L->tau16.p; p.tmin = L->tmin.p; p.span = L->span.p; p.nodeidx = L->nodeidx.p;
@@ -135,7 +197,7 @@ int qmb_lut_build(qmb_ctx *ctx, qmb_lut *L, const int32_t *d_raw) {
   QMB_CUDA(cudaGetLastError());
   int h_stats[4] = {0, 0, 0, 0};
   QMB_CUDA(cudaMemcpyAsync(h_stats, d_stats, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  QMB_CUDA(cudaStreamSynchronize(ctx->stream));
+  QMB_CUDA(cudaStreamSynchronize(ctx->stream));  // also: `boxes` (host vector) was read by the H2D copy
   cudaFree(d_stats);
   L->max_tau = h_stats[0];
   L->max_span = h_stats[1];

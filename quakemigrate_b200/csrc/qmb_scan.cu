@@ -30,6 +30,8 @@
 // re-evaluated stack of the winner.
 #include <math.h>
 
+#include <algorithm>
+
 #include "qmb_internal.cuh"
 
 namespace {
@@ -368,18 +370,15 @@ struct ExactParams {
   int S, Spad;
   const uint16_t *tau16;
   const int32_t *tmin;
-  int nxl, ny, nz, tx, ty, tz, NB, nty, ntz;
+  const uint32_t *slotmap;  // [n_local] tile * NB + slot
+  int NB;
   long long node_offset, n_local;
 };
 
 // stack(node, t) in float64; node is a GLOBAL flat index owned by this rank
 __device__ double exact_stack(const ExactParams &e, long long gnode, long long t) {
-  const long long local = gnode - e.node_offset;
-  const int iz = (int)(local % e.nz);
-  const int iy = (int)((local / e.nz) % e.ny);
-  const int ix = (int)(local / ((long long)e.nz * e.ny));
-  const int j = ((ix / e.tx) * e.nty + (iy / e.ty)) * e.ntz + (iz / e.tz);
-  const int q = ((ix % e.tx) * e.ty + (iy % e.ty)) * e.tz + (iz % e.tz);
+  const uint32_t where = e.slotmap[gnode - e.node_offset];
+  const int j = (int)(where / (uint32_t)e.NB), q = (int)(where % (uint32_t)e.NB);
   double acc = 0.0;
   for (int s = 0; s < e.S; ++s) {
     const size_t m = (size_t)j * e.Spad + s;
@@ -700,8 +699,8 @@ int qmb_scan_run(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, int32_t fsmp, int32_t 
   ExactParams e = {};
   e.on64 = O->log64.p; e.row_stride = O->stride; e.origin = O->front + fsmp;
   e.S = L->S; e.Spad = L->Spad; e.tau16 = L->tau16.p; e.tmin = L->tmin.p;
-  e.nxl = L->nxl; e.ny = L->ny; e.nz = L->nz; e.tx = L->tx; e.ty = L->ty; e.tz = L->tz; e.NB = L->NB;
-  e.nty = L->nty; e.ntz = L->ntz; e.node_offset = L->node_offset; e.n_local = L->n_local;
+  e.slotmap = L->slotmap.p; e.NB = L->NB;
+  e.node_offset = L->node_offset; e.n_local = L->n_local;
   k_exact<<<(int)((T + 127) / 128), 128, 0, ctx->stream>>>(e, ctx->gm1.p, ctx->gm2.p, ctx->gi1.p, ctx->gi2.p,
                                                             thr, shift, T, ctx->ex1.p, ctx->ex2.p);
   ctx->launches++;
@@ -724,6 +723,14 @@ int qmb_scan_run(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, int32_t fsmp, int32_t 
   QMB_CUDA(cudaStreamSynchronize(ctx->stream));
   if (n_slow > slow_cap) n_slow = slow_cap;
   if (n_slow > 0) {
+    // the queue was filled with atomics: put it in ascending sample order so that every rank
+    // (and every run) walks it identically -- the cross-rank fold pairs entries by position
+    std::vector<int> q((size_t)n_slow);
+    QMB_CUDA(cudaMemcpyAsync(q.data(), ctx->slow_list.p + 1, (size_t)n_slow * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    QMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::sort(q.begin(), q.end());
+    QMB_CUDA(cudaMemcpyAsync(ctx->slow_list.p + 1, q.data(), (size_t)n_slow * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    QMB_CUDA(cudaStreamSynchronize(ctx->stream));
     const int ctas = 4 * ctx->sm_count;
     const int n_batches = (n_slow + SLOW_BATCH - 1) / SLOW_BATCH;
     const size_t per_rank = (size_t)n_slow;
