@@ -111,6 +111,18 @@ int qmb_comm_destroy(qmb_ctx_t ctx);
 int qmb_lut_upload(qmb_ctx_t ctx, const int32_t *lut, int32_t nx_local, int32_t ny, int32_t nz,
                    int32_t n_rows, int64_t node_offset, int64_t n_nodes_global, qmb_lut_t *out);
 int qmb_lut_free(qmb_lut_t lut);
+
+/* LUT.serve_traveltimes on the device (quakemigrate/lut/lut.py:502-538).  Upload every
+ * (station, phase) float64 travel-time grid [seconds, (n_grids, nx, ny, nz) C-order] once; then
+ * each availability pattern is served without touching the host: row r of the table is
+ * rint(grids[rows[r]] * sampling_rate) as int32 (negative -> 0), for the x-slab [x0, x1)
+ * (x1 <= 0 means nx).  The result is identical to qmb_lut_upload of the host-served array. */
+typedef struct qmb_ttgrids *qmb_ttgrids_t;
+int qmb_ttgrids_upload(qmb_ctx_t ctx, const double *grids, int32_t n_grids, int32_t nx, int32_t ny,
+                       int32_t nz, qmb_ttgrids_t *out);
+int qmb_ttgrids_free(qmb_ttgrids_t grids);
+int qmb_lut_serve(qmb_ctx_t ctx, qmb_ttgrids_t grids, const int32_t *rows, int32_t n_rows,
+                  double sampling_rate, int32_t x0, int32_t x1, qmb_lut_t *out);
 typedef struct {
   int64_t n_nodes_local, n_nodes_global, node_offset;
   int32_t n_rows, max_tau, max_tile_span, n_tiles, nodes_per_tile;

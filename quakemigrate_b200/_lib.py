@@ -81,6 +81,11 @@ SIGNATURES = {
     "qmb_lut_upload": (ctypes.c_int, [c_void_p, c_i32Pt, c_int32, c_int32, c_int32, c_int32, c_int64,
                                       c_int64, ctypes.POINTER(c_void_p)]),
     "qmb_lut_free": (ctypes.c_int, [c_void_p]),
+    "qmb_ttgrids_upload": (ctypes.c_int, [c_void_p, c_dPt, c_int32, c_int32, c_int32, c_int32,
+                                          ctypes.POINTER(c_void_p)]),
+    "qmb_ttgrids_free": (ctypes.c_int, [c_void_p]),
+    "qmb_lut_serve": (ctypes.c_int, [c_void_p, c_void_p, c_i32Pt, c_int32, c_double, c_int32, c_int32,
+                                     ctypes.POINTER(c_void_p)]),
     "qmb_lut_info": (ctypes.c_int, [c_void_p, ctypes.POINTER(LutInfo)]),
     "qmb_onsets_upload": (ctypes.c_int, [c_void_p, c_dPt, c_int32, c_int64, ctypes.POINTER(c_void_p)]),
     "qmb_onsets_from_waveforms": (ctypes.c_int, [c_void_p, c_dPt, c_int32, c_int64, c_int32, c_i32Pt,

@@ -24,7 +24,7 @@ from . import _lib
 from ._lib import QmbError, c_int32, c_int64, stalta_header_t  # noqa: F401
 
 __all__ = ["migrate", "find_max_coa", "overlapping_sta_lta", "centred_sta_lta",
-           "recursive_sta_lta", "Engine", "DeviceLUT", "DeviceOnsets", "QmbError"]
+           "recursive_sta_lta", "Engine", "DeviceLUT", "DeviceOnsets", "DeviceGrids", "QmbError"]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -143,6 +143,24 @@ class DeviceLUT:
             pass
 
 
+class DeviceGrids:
+    """Handle to float64 travel-time grids (seconds) resident on the device."""
+
+    def __init__(self, engine, handle, shape):
+        self.engine, self._h, self.shape = engine, handle, tuple(shape)
+
+    def free(self):
+        if self._h:
+            _lib.load().qmb_ttgrids_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class DeviceOnsets:
     """Handle to log-onset rows resident on the device."""
 
@@ -235,6 +253,28 @@ class Engine:
         _lib.check(self._lib.qmb_lut_upload(self._h, tt, nx, ny, nz, s, int(node_offset), n_glob,
                                             ctypes.byref(h)))
         return DeviceLUT(self, h, tt.shape, int(node_offset), n_glob)
+
+    def upload_traveltime_grids(self, grids: np.ndarray) -> "DeviceGrids":
+        """``grids``: float64 (n_grids, nx, ny, nz) travel times in seconds, kept on the device."""
+        g = np.ascontiguousarray(grids, dtype=np.double)
+        if g.ndim != 4:
+            raise ValueError("grids must have shape (n_grids, nx, ny, nz)")
+        h = ctypes.c_void_p()
+        _lib.check(self._lib.qmb_ttgrids_upload(self._h, g, *g.shape, ctypes.byref(h)))
+        return DeviceGrids(self, h, g.shape)
+
+    def serve_lut(self, grids: "DeviceGrids", rows, sampling_rate, x_range=None) -> DeviceLUT:
+        """
+        ``LUT.serve_traveltimes`` on the device: onset row r uses grid ``rows[r]``;
+        tau = rint(tt * sampling_rate) as int32 (lut.py:538).  ``x_range`` selects a node slab.
+        """
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        n_grids, nx, ny, nz = grids.shape
+        x0, x1 = (0, nx) if x_range is None else x_range
+        h = ctypes.c_void_p()
+        _lib.check(self._lib.qmb_lut_serve(self._h, grids._h, rows, len(rows), float(sampling_rate),
+                                           int(x0), int(x1), ctypes.byref(h)))
+        return DeviceLUT(self, h, (x1 - x0, ny, nz, len(rows)), x0 * ny * nz, nx * ny * nz)
 
     def upload_onsets(self, onsets: np.ndarray) -> DeviceOnsets:
         """``onsets``: float64 (n_rows, n_total) LINEAR onsets (clip + log happen on the device)."""

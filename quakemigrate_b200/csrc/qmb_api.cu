@@ -270,6 +270,83 @@ extern "C" int qmb_lut_upload(qmb_ctx_t ctx, const int32_t *lut, int32_t nx_loca
   return QMB_OK;
 }
 
+// --- serving from device-resident float64 grids (LUT.serve_traveltimes on the device) ------------
+extern "C" int qmb_ttgrids_upload(qmb_ctx_t ctx, const double *grids, int32_t n_grids, int32_t nx, int32_t ny,
+                                  int32_t nz, qmb_ttgrids_t *out) {
+  if (!ctx || !grids || !out) QMB_FAIL(QMB_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (n_grids <= 0 || nx <= 0 || ny <= 0 || nz <= 0) QMB_FAIL(QMB_ERR_ARG, "empty travel-time grids");
+  QMB_CUDA(cudaSetDevice(ctx->device));
+  qmb_ttgrids *G = new qmb_ttgrids();
+  G->ctx = ctx; G->device = ctx->device; G->n_grids = n_grids; G->nx = nx; G->ny = ny; G->nz = nz;
+  const size_t count = (size_t)n_grids * nx * ny * nz;
+  int rc = G->tt.ensure(count);
+  if (rc == QMB_OK) {
+    cudaError_t e = cudaMemcpyAsync(G->tt.p, grids, count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      qmb_set_error("H2D of the travel-time grids: %s", cudaGetErrorString(e));
+      rc = QMB_ERR_CUDA;
+    }
+  }
+  if (rc != QMB_OK) {
+    G->tt.release();
+    delete G;
+    return rc;
+  }
+  *out = G;
+  return QMB_OK;
+}
+
+extern "C" int qmb_ttgrids_free(qmb_ttgrids_t G) {
+  if (!G) return QMB_OK;
+  cudaSetDevice(G->device);
+  G->tt.release();
+  delete G;
+  return QMB_OK;
+}
+
+extern "C" int qmb_lut_serve(qmb_ctx_t ctx, qmb_ttgrids_t G, const int32_t *rows, int32_t n_rows,
+                             double sampling_rate, int32_t x0, int32_t x1, qmb_lut_t *out) {
+  if (!ctx || !G || !rows || !out) QMB_FAIL(QMB_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (G->ctx != ctx) QMB_FAIL(QMB_ERR_ARG, "grids belong to a different context");
+  if (n_rows <= 0) QMB_FAIL(QMB_ERR_ARG, "no rows selected");
+  if (x1 <= 0) x1 = G->nx;
+  if (x0 < 0 || x0 >= x1 || x1 > G->nx) QMB_FAIL(QMB_ERR_ARG, "x-slab [%d, %d) outside [0, %d)", x0, x1, G->nx);
+  for (int r = 0; r < n_rows; ++r)
+    if (rows[r] < 0 || rows[r] >= G->n_grids) QMB_FAIL(QMB_ERR_ARG, "row %d selects grid %d of %d", r, rows[r], G->n_grids);
+  if (!(sampling_rate > 0)) QMB_FAIL(QMB_ERR_ARG, "sampling rate must be positive");
+  QMB_CUDA(cudaSetDevice(ctx->device));
+  const int64_t plane = (int64_t)G->ny * G->nz;
+  qmb_lut *L = new qmb_lut();
+  L->ctx = ctx; L->device = ctx->device;
+  L->nxl = x1 - x0; L->ny = G->ny; L->nz = G->nz; L->S = n_rows;
+  L->node_offset = x0 * plane; L->n_global = (int64_t)G->nx * plane; L->n_local = (int64_t)(x1 - x0) * plane;
+  if (L->n_global >= 0xFFFFFFFFLL) {
+    delete L;
+    QMB_FAIL(QMB_ERR_UNSUPPORTED, "more than 2^32-2 nodes");
+  }
+  int *d_rows = nullptr;
+  cudaError_t e = cudaMalloc((void **)&d_rows, n_rows * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_rows, rows, n_rows * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+  int rc = QMB_OK;
+  if (e != cudaSuccess) {
+    qmb_set_error("row selection upload: %s", cudaGetErrorString(e));
+    rc = QMB_ERR_CUDA;
+  }
+  QmbServeSource src = {G->tt.p, d_rows, sampling_rate, (long long)L->n_global, (long long)L->node_offset};
+  if (rc == QMB_OK) rc = qmb_lut_build(ctx, L, nullptr, &src);
+  cudaStreamSynchronize(ctx->stream);
+  if (d_rows) cudaFree(d_rows);
+  if (rc != QMB_OK) {
+    qmb_lut_free(L);
+    return rc;
+  }
+  *out = L;
+  return QMB_OK;
+}
+
 extern "C" int qmb_lut_free(qmb_lut_t L) {
   if (!L) return QMB_OK;
   cudaSetDevice(L->device);

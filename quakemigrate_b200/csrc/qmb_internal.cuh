@@ -136,6 +136,13 @@ struct qmb_lut {
   DevBuf<uint32_t> slotmap; // [n_local]             tile * NB + slot of each local node
 };
 
+struct qmb_ttgrids {  // every (station, phase) travel-time grid, float64 seconds, on the device
+  qmb_ctx *ctx = nullptr;
+  int device = 0;
+  int32_t n_grids = 0, nx = 0, ny = 0, nz = 0;
+  DevBuf<double> tt;  // [n_grids][nx*ny*nz]
+};
+
 struct qmb_onsets {
   qmb_ctx *ctx = nullptr;
   int device = 0;
@@ -154,7 +161,13 @@ constexpr int64_t QMB_ONSET_TAIL = 1024;   // trailing zero pad: >= time tile + 
 // ---------------------------------------------------------------------------------------------
 // cross-file entry points
 // ---------------------------------------------------------------------------------------------
-int qmb_lut_build(qmb_ctx *ctx, qmb_lut *L, const int32_t *d_raw);
+struct QmbServeSource {  // float64 travel-time grids resident on the device (qmb_ttgrids)
+  const double *tt;
+  const int *rowsel;
+  double sr;
+  long long stride, node0;
+};
+int qmb_lut_build(qmb_ctx *ctx, qmb_lut *L, const int32_t *d_raw, const QmbServeSource *src = nullptr);
 int qmb_onsets_prepare(qmb_ctx *ctx, qmb_onsets *O, const double *d_linear /* (S,P) */, int already_log);
 int qmb_scan_run(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, int32_t fsmp, int32_t lsmp,
                  int32_t available, float *kernel_ms);

@@ -18,7 +18,11 @@ constexpr int LT_THREADS = 128;
 constexpr int LT_ROWS = 32;  // rows handled per pass through shared memory
 
 struct LutTileParams {
-  const int32_t *raw;  // (nxl*ny*nz, S)
+  const int32_t *raw;  // (nxl*ny*nz, S), or nullptr when serving from float64 grids:
+  const double *tt;    //   seconds, [grid][node of the FULL grid]
+  const int *rowsel;   //   grid index of onset row s
+  double sr;           //   samples per second: tau = rint(tt * sr)  (lut.py:538)
+  long long tt_stride, tt_node0;  // nodes per grid; flat index of this slab's first node
   int nxl, ny, nz, S, Spad;
   int NB;
   const int *boxes;    // [n_tiles][9]: origin x0,y0,z0; tile shape sx,sy,sz; region end x1,y1,z1
@@ -63,7 +67,11 @@ __global__ void __launch_bounds__(LT_THREADS) k_lut_tile(LutTileParams p) {
     for (int q = warp; q < p.NB; q += NWARPS) {
       const int s = s0 + lane;
       int v = 0;
-      if (s < p.S) v = max(0, p.raw[s_node[q] * p.S + s]);
+      if (s < p.S) {
+        if (p.raw) v = p.raw[s_node[q] * p.S + s];
+        else v = (int)rint(p.tt[(size_t)p.rowsel[s] * p.tt_stride + p.tt_node0 + s_node[q]] * p.sr);
+        v = max(0, v);
+      }
       s_tau[lane][q] = v;
     }
     __syncthreads();
@@ -143,7 +151,7 @@ void tile_region(const Region &r, int sx, int sy, int sz, std::vector<int> &boxe
 
 }  // namespace
 
-int qmb_lut_build(qmb_ctx *ctx, qmb_lut *L, const int32_t *d_raw) {
+int qmb_lut_build(qmb_ctx *ctx, qmb_lut *L, const int32_t *d_raw, const QmbServeSource *src) {
   L->v = QMB_VARIANTS[ctx->variant];
   L->tx = L->v.tx;
   L->ty = L->v.ty;
@@ -182,8 +190,11 @@ int qmb_lut_build(qmb_ctx *ctx, qmb_lut *L, const int32_t *d_raw) {
   QMB_CUDA(cudaMalloc((void **)&d_stats, 4 * sizeof(int)));
   QMB_CUDA(cudaMemsetAsync(d_stats, 0, 4 * sizeof(int), ctx->stream));
 
-  LutTileParams p;
+  LutTileParams p = {};
   p.raw = d_raw;
+  if (src) {
+    p.tt = src->tt; p.rowsel = src->rowsel; p.sr = src->sr; p.tt_stride = src->stride; p.tt_node0 = src->node0;
+  }
   p.nxl = L->nxl; p.ny = L->ny; p.nz = L->nz; p.S = L->S; p.Spad = L->Spad;
   p.NB = L->NB;
   p.boxes = L->boxes.p;

@@ -100,6 +100,34 @@ class LUT(Grid3D):
         """lut.py:842-845."""
         return np.max(self._serve_traveltimes(self.phases))
 
+    # -- device-resident serving (the reference re-stacks and re-rounds on every call) --------
+    def grid_index(self):
+        """``{(station, phase): i}`` in the phase-outer / station-inner order of lut.py:576-603."""
+        index = {}
+        for phase in self.phases:
+            for station in self.stations:
+                tts = self[station]
+                if phase in tts or f"TIME_{phase}" in tts:
+                    index[(station, phase)] = len(index)
+        return index
+
+    def to_device(self, engine):
+        """Upload every float64 grid once; returns ``(DeviceGrids, grid_index)``."""
+        index = self.grid_index()
+        stack = np.stack([self[st][ph] if ph in self[st] else self[st][f"TIME_{ph}"]
+                          for (st, ph) in index], axis=0)
+        return engine.upload_traveltime_grids(stack), index
+
+    @staticmethod
+    def rows_for(availability, index):
+        """Grid index per served row for an availability dict (lut.py:527-537 ordering)."""
+        rows = []
+        for key, available in availability.items():
+            station, phase = key.split("_")
+            if available == 1:
+                rows.append(index[(station, phase)])   # KeyError -> missing phase, like the reference
+        return rows
+
 
 # ------------------------------------------------------------------------------------------------
 # reading the reference's pickled LUTs without pyproj

@@ -82,21 +82,31 @@ class QuakeScan:
         self.scan_rate = kwargs.get("scan_rate", self.onset.sampling_rate)
         self.pre_pad = self.post_pad = 0.0
         self._lut_cache: dict = {}
+        # serve the int32 table on the device from resident float64 grids when the LUT can
+        self.serve_on_device = kwargs.get("serve_on_device", hasattr(lut, "to_device"))
+        self._grids = None
 
     # -- travel-time cache -----------------------------------------------------------------------
     def _device_lut(self, sampling_rate, availability):
         key = (int(sampling_rate), tuple(availability.items()))
         if key not in self._lut_cache:
+            if len(self._lut_cache) >= 4:  # bound device memory: drop the oldest pattern
+                old = next(iter(self._lut_cache))
+                self._lut_cache.pop(old).free()
             try:
-                traveltimes = self.lut.serve_traveltimes(sampling_rate, availability)
+                if self.serve_on_device:
+                    if self._grids is None:
+                        self._grids = self.lut.to_device(self.engine)
+                    grids, index = self._grids
+                    rows = self.lut.rows_for(availability, index)
+                    self._lut_cache[key] = self.engine.serve_lut(grids, rows, sampling_rate)
+                else:
+                    traveltimes = self.lut.serve_traveltimes(sampling_rate, availability)
+                    self._lut_cache[key] = self.engine.upload_lut(traveltimes)
             except KeyError as e:
                 raise LUTPhasesException(
                     f"Attempting to migrate phases; but traveltimes for {e} not found in the LUT."
                 )
-            if len(self._lut_cache) >= 4:  # bound device memory: drop the oldest pattern
-                old = next(iter(self._lut_cache))
-                self._lut_cache.pop(old).free()
-            self._lut_cache[key] = self.engine.upload_lut(traveltimes)
         return self._lut_cache[key]
 
     def set_pads(self, timespan: float):
@@ -198,3 +208,6 @@ class QuakeScan:
         for dlut in self._lut_cache.values():
             dlut.free()
         self._lut_cache.clear()
+        if self._grids is not None:
+            self._grids[0].free()
+            self._grids = None

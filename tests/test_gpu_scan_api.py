@@ -101,3 +101,35 @@ def test_compute_detect_and_locate(position):
     np.testing.assert_allclose(coa_map, r_coa_map / np.nanmax(r_coa_map), rtol=1e-5)
     scan.close()
     eng.close()
+
+
+def test_device_served_table_equals_host_served():
+    """qmb_lut_serve == qmb_lut_upload(LUT.serve_traveltimes(...)) (lut.py:502-538), incl. x-slabs."""
+    from quakemigrate_b200.core import Engine
+    cfg, prob, lut, data = _problem()
+    eng = Engine(0)
+    avail = {f"ST{k:03d}_{ph}": (0 if (k, ph) in ((1, "P"), (3, "S")) else 1) for ph in ("P", "S") for k in range(4)}
+    host = lut.serve_traveltimes(cfg.sampling_rate, avail)
+    grids, index = lut.to_device(eng)
+    rows = lut.rows_for(avail, index)
+    a = eng.upload_lut(host)
+    b = eng.serve_lut(grids, rows, cfg.sampling_rate)
+    ia, ib = a.info(), b.info()
+    for k in ("n_rows", "max_tau", "max_tile_span", "n_tiles", "n_nodes_local"):
+        assert ia[k] == ib[k], k
+    onsets, _ = syn.random_problem(9, cfg.grid, host.shape[-1], 300, 10, int(host.max()) + 5)
+    ra = eng.detect(a, onsets, 10, int(host.max()) + 5, host.shape[-1])
+    rb = eng.detect(b, onsets, 10, int(host.max()) + 5, host.shape[-1])
+    for x, y in zip(ra, rb):
+        assert np.array_equal(x, y)
+    # slab form: the second half of the x-planes
+    x0 = cfg.grid[0] // 2
+    c = eng.serve_lut(grids, rows, cfg.sampling_rate, x_range=(x0, cfg.grid[0]))
+    d = eng.upload_lut(host[x0:], node_offset=x0 * cfg.grid[1] * cfg.grid[2], n_nodes_global=cfg.n_nodes)
+    rc = eng.detect(c, onsets, 10, int(host.max()) + 5, host.shape[-1])
+    rd = eng.detect(d, onsets, 10, int(host.max()) + 5, host.shape[-1])
+    for x, y in zip(rc, rd):
+        assert np.array_equal(x, y)
+    with pytest.raises(KeyError):
+        lut.rows_for({"ST000_X": 1}, index)
+    eng.close()
