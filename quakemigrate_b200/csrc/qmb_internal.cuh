@@ -40,20 +40,21 @@ void qmb_set_error(const char *fmt, ...);
 // Scan-kernel variants: W consumer warps x NPW nodes per warp form a node tile of tx*ty*tz nodes;
 // every lane carries K time samples, so a time tile is 32*K samples.
 struct QmbVariant {
-  int id, W, NPW, K, tx, ty, tz;
+  int id, W, NPW, K, tx, ty, tz, CR;  // CR = onset rows staged per pipeline stage
 };
-constexpr int QMB_N_VARIANTS = 7;
+constexpr int QMB_N_VARIANTS = 8;
 constexpr QmbVariant QMB_VARIANTS[QMB_N_VARIANTS] = {
-    {0, 16, 4, 8, 4, 4, 4},  // 17 warps -> 96 regs/thread
-    {1, 16, 8, 4, 4, 4, 8},
-    {2, 8, 8, 8, 4, 4, 4},   // 9 warps -> 168 regs/thread
-    {3, 8, 8, 4, 4, 4, 4},
-    {4, 12, 4, 8, 4, 4, 3},  // 13 warps -> 128 regs/thread
-    {5, 12, 8, 4, 4, 4, 6},
-    {6, 8, 4, 8, 4, 4, 2},
+    {0, 16, 4, 8, 4, 4, 4, 16},  // 17 warps -> 96 regs/thread
+    {1, 16, 8, 4, 4, 4, 8, 16},
+    {2, 8, 8, 8, 4, 4, 4, 16},   // 9 warps -> 168 regs/thread
+    {3, 8, 8, 4, 4, 4, 4, 16},
+    {4, 12, 4, 8, 4, 4, 3, 16},  // 13 warps -> 128 regs/thread
+    {5, 12, 8, 4, 4, 4, 6, 16},
+    {6, 8, 4, 8, 4, 4, 2, 16},
+    {7, 12, 4, 8, 4, 4, 3, 32},  // as 4, 32 rows per stage: half the stage hand-offs
 };
-constexpr int QMB_DEFAULT_VARIANT = 4;  // measured best on B200 (scripts/sweep_variants.sh)
-constexpr int QMB_CHUNK_ROWS = 16;      // onset rows (station x phase) staged per pipeline stage
+constexpr int QMB_DEFAULT_VARIANT = 7;  // measured best on B200 (scripts/sweep_variants.sh)
+constexpr int QMB_DEFAULT_CHUNK_ROWS = 16;  // onset rows (station x phase) staged per pipeline stage
 constexpr int QMB_SMEM_BUDGET = 227 * 1024;
 
 // ---------------------------------------------------------------------------------------------
@@ -122,7 +123,7 @@ struct qmb_ctx {
 struct qmb_lut {
   qmb_ctx *ctx = nullptr;
   int device = 0;  // copied from ctx: handles may outlive their context
-  int32_t nxl = 0, ny = 0, nz = 0, S = 0, Spad = 0;
+  int32_t nxl = 0, ny = 0, nz = 0, S = 0, Spad = 0, chunk_rows = QMB_DEFAULT_CHUNK_ROWS;
   int64_t node_offset = 0, n_global = 0, n_local = 0;
   QmbVariant v = QMB_VARIANTS[QMB_DEFAULT_VARIANT];  // variant this table was tiled for
   int tx = 4, ty = 4, tz = 4, NB = 64;

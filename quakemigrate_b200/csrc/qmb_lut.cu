@@ -179,7 +179,8 @@ int qmb_lut_build(qmb_ctx *ctx, qmb_lut *L, const int32_t *d_raw, const QmbServe
   QMB_TRY(L->boxes.ensure(boxes.size()));
   QMB_TRY(L->slotmap.ensure((size_t)L->n_local));
   QMB_CUDA(cudaMemcpyAsync(L->boxes.p, boxes.data(), boxes.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  L->Spad = ((L->S + QMB_CHUNK_ROWS - 1) / QMB_CHUNK_ROWS) * QMB_CHUNK_ROWS;
+  L->chunk_rows = L->v.CR;
+  L->Spad = ((L->S + L->chunk_rows - 1) / L->chunk_rows) * L->chunk_rows;
 
   QMB_TRY(L->tau16.ensure((size_t)L->n_tiles * L->Spad * L->NB));
   QMB_TRY(L->tmin.ensure((size_t)L->n_tiles * L->Spad));

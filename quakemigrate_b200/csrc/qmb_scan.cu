@@ -30,6 +30,8 @@
 // re-evaluated stack of the winner.
 #include <math.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "qmb_internal.cuh"
@@ -93,7 +95,7 @@ struct ScanParams {
   const float *on32;     // [S][row_stride]
   long long row_stride;  // elements
   long long t_origin;    // index within a row of (tau = 0, sample t' = 0); multiple of 4
-  int S, n_chunks;
+  int S, n_chunks, chunk_rows;
   // LUT tiles
   const uint16_t *tau16;
   const int32_t *tmin;
@@ -121,7 +123,7 @@ struct ScanParams {
   double avail;
 };
 
-template <int W, int NPW, int K, int MODE>
+template <int W, int NPW, int K, int MODE, int CR>
 __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
   constexpr int NB = W * NPW;
   constexpr int TT = 32 * K;
@@ -130,8 +132,8 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
 
   // stage layout: [16 rows x RS floats][16 x NB uint16 tau][NB uint32 node index]
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t rows_bytes = (uint32_t)QMB_CHUNK_ROWS * p.RS * 4u;
-  const uint32_t tau_bytes = (uint32_t)QMB_CHUNK_ROWS * NB * 2u;
+  const uint32_t rows_bytes = (uint32_t)CR * p.RS * 4u;
+  constexpr uint32_t tau_bytes = (uint32_t)CR * NB * 2u;
   const uint32_t bar_base = smem_base + (uint32_t)p.n_stages * p.stage_bytes;  // full[], then empty[]
 
   if (threadIdx.x == 0) {
@@ -151,13 +153,13 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
     // ===================================== producer ==========================================
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const int r = it / p.n_time_tiles, tt = it - r * p.n_time_tiles;
-      const int tile0 = r * p.tiles_per_item;
-      const int tile1 = min(p.n_tiles, tile0 + p.tiles_per_item);
+      const int tile0 = (int)((long long)r * p.n_tiles / p.R);
+      const int tile1 = (int)((long long)(r + 1) * p.n_tiles / p.R);
       const long long tbase = p.t_origin + (long long)tt * TT;
       for (int j = tile0; j < tile1; ++j) {
         for (int c = 0; c < p.n_chunks; ++c) {
-          const int s = c * QMB_CHUNK_ROWS + lane;
-          const bool act = lane < QMB_CHUNK_ROWS && s < p.S;
+          const int s = c * CR + lane;
+          const bool act = lane < CR && s < p.S;
           // metadata loads are issued before the wait so their latency overlaps it
           int tmin = 0, len = 0;
           if (act) {
@@ -177,10 +179,10 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
           if (act)
             bulk_g2s(stage + (uint32_t)lane * p.RS * 4u, p.on32 + (size_t)s * p.row_stride + tbase + tmin,
                      bytes, full);
-          if (lane == 16)
-            bulk_g2s(stage + rows_bytes, p.tau16 + ((size_t)j * p.Spad + (size_t)c * QMB_CHUNK_ROWS) * NB,
+          if (lane == 0)
+            bulk_g2s(stage + rows_bytes, p.tau16 + ((size_t)j * p.Spad + (size_t)c * CR) * NB,
                      tau_bytes, full);
-          if (lane == 17 && c == 0)
+          if (lane == 1 && c == 0)
             bulk_g2s(stage + rows_bytes + tau_bytes, p.nodeidx + (size_t)j * NB, NB * 4u, full);
           if (++st == p.n_stages) { st = 0; ph ^= 1u; }
         }
@@ -193,8 +195,8 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
   const float NEG_INF = __int_as_float(0xff800000);
   for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
     const int r = it / p.n_time_tiles, tt = it - r * p.n_time_tiles;
-    const int tile0 = r * p.tiles_per_item;
-    const int tile1 = min(p.n_tiles, tile0 + p.tiles_per_item);
+    const int tile0 = (int)((long long)r * p.n_tiles / p.R);
+    const int tile1 = (int)((long long)(r + 1) * p.n_tiles / p.R);
 
     float m1[K], m2[K], m3[K];
     uint32_t i1[K], i2[K];
@@ -224,12 +226,14 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
           for (int q = 0; q < NPW; ++q)
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(nidx[q]) : "r"(ia + 4u * q));
         }
-        const int nrows = min(QMB_CHUNK_ROWS, p.S - c * QMB_CHUNK_ROWS);
+        const int nrows = min(CR, p.S - c * CR);
         const uint32_t tau_addr = stage + rows_bytes + (uint32_t)(warp * NPW) * 2u;
         uint32_t row_addr = stage + (uint32_t)lane * 4u;
-#pragma unroll 2
-        for (int sl = 0; sl < nrows; ++sl) {
-          uint32_t off[NPW];
+        // Software-pipelined over rows with a half-row skew: the gathers of one half of the
+        // warp's nodes are always in flight while the other half is being accumulated, so at
+        // least NPW*K/2 independent LDS are outstanding whatever order ptxas picks.
+        constexpr int H = NPW / 2;
+        auto load_off = [&](int sl, uint32_t (&off)[NPW]) {
           if constexpr (NPW == 4) {
             uint32_t a, b;
             asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(tau_addr + (uint32_t)sl * NB * 2u));
@@ -242,20 +246,39 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
             off[0] = a & 0xffffu; off[1] = a >> 16; off[2] = b & 0xffffu; off[3] = b >> 16;
             off[4] = cc & 0xffffu; off[5] = cc >> 16; off[6] = d & 0xffffu; off[7] = d >> 16;
           }
-          // issue the whole batch of gathers before the adds: NPW*K independent LDS in flight
-          float v[NPW][K];
+        };
+        auto load_half = [&](int h, const uint32_t (&off)[NPW], uint32_t base, float (&v)[H][K]) {
 #pragma unroll
-          for (int q = 0; q < NPW; ++q) {
-            const uint32_t a = row_addr + off[q] * 4u;
+          for (int q = 0; q < H; ++q) {
+            const uint32_t a = base + off[h * H + q] * 4u;
 #pragma unroll
             for (int k = 0; k < K; ++k) v[q][k] = lds_f32(a + 128u * k);
           }
+        };
+        auto add_half = [&](int h, const float (&v)[H][K]) {
 #pragma unroll
-          for (int q = 0; q < NPW; ++q)
+          for (int q = 0; q < H; ++q)
 #pragma unroll
-            for (int k = 0; k < K; ++k) acc[q][k] += v[q][k];
+            for (int k = 0; k < K; ++k) acc[h * H + q][k] += v[q][k];
+        };
+        uint32_t off[NPW], off_next[NPW];
+        float v0[H][K], v1[H][K];
+        load_off(0, off);
+        load_half(0, off, row_addr, v0);
+#pragma unroll 2
+        for (int sl = 0; sl + 1 < nrows; ++sl) {
+          load_half(1, off, row_addr, v1);
+          load_off(sl + 1, off_next);
+          add_half(0, v0);
           row_addr += (uint32_t)p.RS * 4u;
+          load_half(0, off_next, row_addr, v0);
+          add_half(1, v1);
+#pragma unroll
+          for (int q = 0; q < NPW; ++q) off[q] = off_next[q];
         }
+        load_half(1, off, row_addr, v1);
+        add_half(0, v0);
+        add_half(1, v1);
         __syncwarp();
         if (lane == 0) mbar_arrive(empty);
         if (++st == p.n_stages) { st = 0; ph ^= 1u; }
@@ -525,10 +548,10 @@ __global__ void k_slow_scatter(const int *slow_list, int n_slow, const double *v
   r_norm[t] = val[b] * n_nodes_global / gsum[t + shift];
 }
 
-template <int W, int NPW, int K, int MODE>
+template <int W, int NPW, int K, int MODE, int CR>
 int launch_scan(qmb_ctx *ctx, const ScanParams &p, int grid, size_t smem) {
-  QMB_CUDA(cudaFuncSetAttribute(k_scan<W, NPW, K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_scan<W, NPW, K, MODE><<<grid, (W + 1) * 32, smem, ctx->stream>>>(p);
+  QMB_CUDA(cudaFuncSetAttribute(k_scan<W, NPW, K, MODE, CR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_scan<W, NPW, K, MODE, CR><<<grid, (W + 1) * 32, smem, ctx->stream>>>(p);
   ctx->launches++;
   QMB_CUDA(cudaGetLastError());
   return QMB_OK;
@@ -537,13 +560,14 @@ int launch_scan(qmb_ctx *ctx, const ScanParams &p, int grid, size_t smem) {
 template <int MODE>
 int dispatch_scan(qmb_ctx *ctx, const QmbVariant &v, const ScanParams &p, int grid, size_t smem) {
   switch (v.id) {
-    case 0: return launch_scan<16, 4, 8, MODE>(ctx, p, grid, smem);
-    case 1: return launch_scan<16, 8, 4, MODE>(ctx, p, grid, smem);
-    case 2: return launch_scan<8, 8, 8, MODE>(ctx, p, grid, smem);
-    case 3: return launch_scan<8, 8, 4, MODE>(ctx, p, grid, smem);
-    case 4: return launch_scan<12, 4, 8, MODE>(ctx, p, grid, smem);
-    case 5: return launch_scan<12, 8, 4, MODE>(ctx, p, grid, smem);
-    case 6: return launch_scan<8, 4, 8, MODE>(ctx, p, grid, smem);
+    case 0: return launch_scan<16, 4, 8, MODE, 16>(ctx, p, grid, smem);
+    case 1: return launch_scan<16, 8, 4, MODE, 16>(ctx, p, grid, smem);
+    case 2: return launch_scan<8, 8, 8, MODE, 16>(ctx, p, grid, smem);
+    case 3: return launch_scan<8, 8, 4, MODE, 16>(ctx, p, grid, smem);
+    case 4: return launch_scan<12, 4, 8, MODE, 16>(ctx, p, grid, smem);
+    case 5: return launch_scan<12, 8, 4, MODE, 16>(ctx, p, grid, smem);
+    case 6: return launch_scan<8, 4, 8, MODE, 16>(ctx, p, grid, smem);
+    case 7: return launch_scan<12, 4, 8, MODE, 32>(ctx, p, grid, smem);
   }
   QMB_FAIL(QMB_ERR_ARG, "unknown kernel variant %d", v.id);
 }
@@ -565,11 +589,12 @@ static int scan_setup(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, long long first, 
   p.T = T;
   p.t_origin = O->front + first - shift;
   p.S = L->S;
-  p.n_chunks = L->Spad / QMB_CHUNK_ROWS;
+  p.chunk_rows = L->chunk_rows;
+  p.n_chunks = L->Spad / L->chunk_rows;
   p.tau16 = L->tau16.p; p.tmin = L->tmin.p; p.span = L->span.p; p.nodeidx = L->nodeidx.p;
   p.n_tiles = L->n_tiles; p.Spad = L->Spad;
   p.RS = ((L->max_span + TT + 3) & ~3) + 4;
-  p.stage_bytes = QMB_CHUNK_ROWS * p.RS * 4 + QMB_CHUNK_ROWS * NB * 2 + NB * 4;
+  p.stage_bytes = L->chunk_rows * p.RS * 4 + L->chunk_rows * NB * 2 + NB * 4;
   p.stage_bytes = (p.stage_bytes + 127) & ~127;
   const int avail_smem = QMB_SMEM_BUDGET - 1024;
   p.n_stages = avail_smem / (p.stage_bytes + 16);
@@ -578,14 +603,31 @@ static int scan_setup(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, long long first, 
     QMB_FAIL(QMB_ERR_UNSUPPORTED, "travel-time range inside a node tile (%d samples) too large for shared memory", L->max_span);
   smem = (size_t)p.n_stages * p.stage_bytes + (size_t)p.n_stages * 16 + 128;
   p.n_time_tiles = (int)((T + shift + TT - 1) / TT);
-  // split nodes into R ranges so that items ~ 32 per SM, each item >= 4 tiles
+  // Items = time tiles x R node ranges (ranges balanced to +-1 tile), dealt round-robin to the
+  // persistent CTAs.  All items cost the same, so the tail loss is 1 - items / (rounds * grid):
+  // pick the R in [R0, 4 R0] that minimises it (>= 8 tiles per item, partial buffers <= 3 GiB).
   const int grid = ctx->sm_count;
-  int R = (32 * grid + p.n_time_tiles - 1) / p.n_time_tiles;
-  const int maxR = (L->n_tiles + 3) / 4;
-  if (R > maxR) R = maxR;
-  if (R < 1) R = 1;
+  const int W = L->v.W;
+  int R0 = (32 * grid + p.n_time_tiles - 1) / p.n_time_tiles;
+  if (R0 < 1) R0 = 1;
+  int maxR = L->n_tiles / 8;
+  if (maxR < 1) maxR = 1;
+  const long long part_bytes_per_R = (long long)W * p.n_time_tiles * TT * 28;
+  const int memR = (int)std::max<long long>(1, (3LL << 30) / std::max<long long>(1, part_bytes_per_R));
+  if (maxR > memR) maxR = memR;
+  if (R0 > maxR) R0 = maxR;
+  int R = R0;
+  double best_eff = -1.0;
+  for (int cand = R0; cand <= std::min(maxR, 4 * R0); ++cand) {
+    const long long items = (long long)cand * p.n_time_tiles;
+    const double eff = (double)items / (double)(((items + grid - 1) / grid) * grid);
+    if (eff > best_eff + 1e-9) { best_eff = eff; R = cand; }
+  }
+  if (const char *env = getenv("QMB_NODE_RANGES")) {  // tuning override
+    const int forced = atoi(env);
+    if (forced >= 1 && forced <= std::max(1, L->n_tiles)) R = forced;
+  }
   p.tiles_per_item = (L->n_tiles + R - 1) / R;
-  R = (L->n_tiles + p.tiles_per_item - 1) / p.tiles_per_item;
   p.R = R;
   p.scale = (float)(1.4426950408889634 / (double)available);
   p.Tpad = (long long)p.n_time_tiles * TT;
