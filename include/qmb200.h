@@ -182,6 +182,23 @@ int qmb_locate_window(qmb_ctx_t ctx, qmb_lut_t lut, qmb_onsets_t onsets, int32_t
                       int32_t lsmp, int32_t available, int32_t win0, int32_t win1,
                       double *coa_map, double *map4d_win);
 
+/* --- locate, 3-D map stage ---------------------------------------------------
+ * Streaming float64 kernels over the (nx, ny, nz) marginalised coalescence map; host pointers in
+ * and out (the map is 8*N bytes).
+ * qmb_gaufilt3d : QuakeScan._gaufilt3d (quakemigrate/signal/scan.py:1008-1043): Gaussian
+ *                 smoothing in scipy fftconvolve(mode="same") semantics, mirrored and repeated,
+ *                 each pass normalised by its maximum.
+ * qmb_map3d_peak: nanargmax (first, C order), nanmax and nanmean of a map (scan.py:869,878,972).
+ * qmb_covfit3d  : reductions of QuakeScan._covfit3d (scan.py:939-1005) over nodes with
+ *                 map > thresh (win <= 0: whole grid; else +-(win-1)//2 nodes around the maximum):
+ *                 out12[0..2] = weighted expectation (index * spacing), out12[3..11] = covariance. */
+int qmb_gaufilt3d(qmb_ctx_t ctx, const double *map3d, int32_t nx, int32_t ny, int32_t nz, double sgm,
+                  double *smoothed);
+int qmb_map3d_peak(qmb_ctx_t ctx, const double *map3d, int64_t n, int64_t *argmax, double *maxval,
+                   double *mean);
+int qmb_covfit3d(qmb_ctx_t ctx, const double *map3d, int32_t nx, int32_t ny, int32_t nz,
+                 const double *spacing, double thresh, int32_t win, double *out12);
+
 #ifdef __cplusplus
 }
 #endif

@@ -310,3 +310,40 @@ def np_stalta_onset(channels, nsta, nlta, position="classic", transform="energy"
     ons = np.array([fn(w, nsta, nlta) for w in tr])
     onset = np.sqrt(np.sum([o ** 2 for o in ons], axis=0) / len(ons))
     return np.clip(onset, min_onset_value, np.inf)
+
+
+# ----------------------------------------------------------------------------------------
+# locate: 3-D map stage -- numpy/scipy restatement, test use only
+# ----------------------------------------------------------------------------------------
+def np_gaussian_3d(nx, ny, nz, sgm):
+    """``util.gaussian_3d`` (quakemigrate/util.py:76-116): samples at -(n-1)/2 .. (n-1)/2."""
+    axes = [np.linspace(-(n - 1) / 2, (n - 1) / 2, n) for n in (nx, ny, nz)]
+    gx, gy, gz = np.meshgrid(*axes, indexing="ij")
+    s = np.repeat(sgm, 3) if np.isscalar(sgm) else np.asarray(sgm)
+    return np.exp(-(gx * gx) / (2 * s[0] ** 2) - (gy * gy) / (2 * s[1] ** 2) - (gz * gz) / (2 * s[2] ** 2))
+
+
+def np_gaufilt3d(map3d, sgm=0.8):
+    """``QuakeScan._gaufilt3d`` (scan.py:1008-1043): smooth, mirror + normalise, twice."""
+    from scipy.signal import fftconvolve
+
+    flt = np_gaussian_3d(*map3d.shape, sgm)
+    out = np.asarray(map3d, dtype=np.double)
+    for _ in range(2):
+        out = fftconvolve(out, flt, mode="same")
+        out = out[::-1, ::-1, ::-1] / np.nanmax(out)
+    return out
+
+
+def np_covfit3d(coa_map, node_spacing, thresh=0.90):
+    """Moments of ``QuakeScan._covfit3d`` (scan.py:966-1001): (expectation, covariance)."""
+    w = np.where(coa_map > thresh, coa_map, np.nan)
+    ssw = np.nansum(w)
+    grids = np.meshgrid(*[np.arange(n) for n in coa_map.shape], indexing="ij")
+    xs = [g * s for g, s in zip(grids, node_spacing)]
+    e = [np.nansum(w * x) / ssw for x in xs]
+    cov = np.empty((3, 3))
+    for i in range(3):
+        for j in range(3):
+            cov[i, j] = np.nansum(w * (xs[i] - e[i]) * (xs[j] - e[j])) / ssw
+    return np.array(e), cov

@@ -100,6 +100,11 @@ SIGNATURES = {
                                   c_dPt, c_dPt, c_i64Pt]),
     "qmb_locate_window": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                          c_int32, c_int32, c_void_p, c_void_p]),
+    "qmb_gaufilt3d": (ctypes.c_int, [c_void_p, c_dPt, c_int32, c_int32, c_int32, c_double, c_dPt]),
+    "qmb_map3d_peak": (ctypes.c_int, [c_void_p, c_dPt, c_int64, ctypes.POINTER(c_int64),
+                                      ctypes.POINTER(c_double), ctypes.POINTER(c_double)]),
+    "qmb_covfit3d": (ctypes.c_int, [c_void_p, c_dPt, c_int32, c_int32, c_int32, c_dPt, c_double, c_int32,
+                                    c_dPt]),
 }
 
 _cdll = None

@@ -359,6 +359,36 @@ class Engine:
                                         int(available), max_coa, max_norm, idx))
         return max_coa, max_norm, idx
 
+    # -- locate: 3-D map stage ---------------------------------------------------------------
+    def gaufilt3d(self, map3d: np.ndarray, sgm: float = 0.8) -> np.ndarray:
+        """``QuakeScan._gaufilt3d`` (scan.py:1008-1043) on the device."""
+        m = np.ascontiguousarray(map3d, dtype=np.double)
+        if m.ndim != 3:
+            raise ValueError("map3d must be 3-D")
+        out = np.empty_like(m)
+        _lib.check(self._lib.qmb_gaufilt3d(self._h, m, *m.shape, float(sgm), out))
+        return out
+
+    def map_peak(self, map3d: np.ndarray):
+        """(nanargmax as ijk tuple, nanmax, nanmean) of a map (scan.py:869,878,972)."""
+        m = np.ascontiguousarray(map3d, dtype=np.double)
+        idx, mx, mean = c_int64(-1), ctypes.c_double(0.0), ctypes.c_double(0.0)
+        _lib.check(self._lib.qmb_map3d_peak(self._h, m.reshape(-1), m.size, ctypes.byref(idx),
+                                            ctypes.byref(mx), ctypes.byref(mean)))
+        return tuple(int(i) for i in np.unravel_index(idx.value, m.shape)), mx.value, mean.value
+
+    def covfit3d(self, map3d: np.ndarray, node_spacing, thresh: float = 0.90, win: int | None = None):
+        """
+        Weighted expectation and covariance of the nodes above ``thresh``
+        (``QuakeScan._covfit3d`` reductions, scan.py:966-1001): returns
+        ``(expectation (3,) in index*spacing units, covariance (3, 3))``.
+        """
+        m = np.ascontiguousarray(map3d, dtype=np.double)
+        sp = np.ascontiguousarray(np.broadcast_to(np.asarray(node_spacing, dtype=np.double), (3,)))
+        out = np.empty(12, dtype=np.double)
+        _lib.check(self._lib.qmb_covfit3d(self._h, m, *m.shape, sp, float(thresh), int(win or 0), out))
+        return out[:3].copy(), out[3:].reshape(3, 3).copy()
+
     # -- locate -----------------------------------------------------------------------------
     def locate_window(self, lut: DeviceLUT, onsets: DeviceOnsets, fsmp: int, lsmp: int, available: int,
                       win0: int, win1: int, return_map4d: bool = False):

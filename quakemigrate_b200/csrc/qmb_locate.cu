@@ -1,0 +1,331 @@
+// qmb_locate.cu -- the 3-D map stage that follows the marginal window in locate()
+// (SURVEY.md section 8f rank 1): streaming float64 kernels over the (nx, ny, nz) marginalised
+// coalescence map.  They restate, on the device,
+//   * QuakeScan._gaufilt3d  (quakemigrate/signal/scan.py:1008-1043): convolve with a full-size
+//     Gaussian (util.gaussian_3d, util.py:76-116) in scipy's mode="same" sense, mirror, normalise
+//     by the maximum, convolve again, mirror, normalise;
+//   * the reductions of QuakeScan._covfit3d (scan.py:939-1005): weighted first moments and
+//     central second moments of the nodes above a threshold (optionally inside a window);
+//   * nanargmax / nanmean of a map (scan.py:869, :878, :972).
+// The small dense algebra that follows (pinv of a 343x10 system, 3x3 eigen-problem, the cubic RBF
+// on a 5^3 window) stays on the host (quakemigrate_b200/locate.py).
+//
+// scipy.signal.fftconvolve(a, g, mode="same") with g the same shape as a returns, per axis of
+// length n,  out[i] = sum_j a[j] * g[i - j + (n-1)//2];  with g[m] = exp(-(m-(n-1)/2)^2 / (2 s^2))
+// this is a Gaussian centred half a sample off when n is even -- the reference mirrors and
+// repeats the convolution to cancel that shift, and so do we.  The Gaussian is separable, so
+// three 1-D passes give the same result as the 3-D FFT product (to rounding, ~1e-16 of the peak).
+#include <math.h>
+
+#include <vector>
+
+#include "qmb_internal.cuh"
+
+namespace {
+
+struct Dims {
+  int nx, ny, nz;
+};
+
+// one 1-D pass along `axis` (0:x, 1:y, 2:z): out[i] = sum_m w[m] * in[i + c - m]
+__global__ void __launch_bounds__(256) k_conv_axis(const double *in, double *out, Dims d, int axis,
+                                                   const double *w, int m_lo, int m_hi, int c) {
+  const long long n_total = (long long)d.nx * d.ny * d.nz;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_total) return;
+  const int iz = (int)(idx % d.nz), iy = (int)((idx / d.nz) % d.ny), ix = (int)(idx / ((long long)d.nz * d.ny));
+  const int n = axis == 0 ? d.nx : (axis == 1 ? d.ny : d.nz);
+  const int i = axis == 0 ? ix : (axis == 1 ? iy : iz);
+  const long long stride = axis == 0 ? (long long)d.ny * d.nz : (axis == 1 ? d.nz : 1);
+  const long long base = idx - (long long)i * stride;
+  double acc = 0.0;
+  for (int m = m_lo; m <= m_hi; ++m) {
+    const int j = i + c - m;
+    if (j >= 0 && j < n) acc += w[m] * in[base + (long long)j * stride];
+  }
+  out[idx] = acc;
+}
+
+// per-block (max ignoring NaN, first index of it, sum of non-NaN, count of non-NaN)
+struct PeakPartial {
+  double mx, sum;
+  long long idx, cnt;
+};
+
+__global__ void __launch_bounds__(256) k_peak_partial(const double *map, long long n, PeakPartial *part) {
+  double mx = -INFINITY, sum = 0.0;
+  long long idx = -1, cnt = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double v = map[i];
+    if (v != v) continue;
+    sum += v;
+    ++cnt;
+    if (v > mx || idx < 0) { mx = v; idx = i; }  // ascending i within a thread: first maximum
+  }
+  __shared__ double s_mx[256], s_sum[256];
+  __shared__ long long s_idx[256], s_cnt[256];
+  const int t = threadIdx.x;
+  s_mx[t] = mx; s_sum[t] = sum; s_idx[t] = idx; s_cnt[t] = cnt;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (t < o) {
+      const double v = s_mx[t + o];
+      const long long j = s_idx[t + o];
+      if (j >= 0 && (s_idx[t] < 0 || v > s_mx[t] || (v == s_mx[t] && j < s_idx[t]))) { s_mx[t] = v; s_idx[t] = j; }
+      s_sum[t] += s_sum[t + o];
+      s_cnt[t] += s_cnt[t + o];
+    }
+    __syncthreads();
+  }
+  if (t == 0) part[blockIdx.x] = {s_mx[0], s_sum[0], s_idx[0], s_cnt[0]};
+}
+
+__global__ void k_peak_final(const PeakPartial *part, int n_parts, PeakPartial *out) {
+  PeakPartial r = {-INFINITY, 0.0, -1, 0};
+  for (int q = 0; q < n_parts; ++q) {  // single thread: deterministic order
+    const PeakPartial p = part[q];
+    r.sum += p.sum;
+    r.cnt += p.cnt;
+    if (p.idx >= 0 && (r.idx < 0 || p.mx > r.mx || (p.mx == r.mx && p.idx < r.idx))) { r.mx = p.mx; r.idx = p.idx; }
+  }
+  *out = r;
+}
+
+// out[mirror(i)] = in[i] * scale   (reverse all three axes == reverse the flat C-order index)
+__global__ void __launch_bounds__(256) k_mirror_scale(const double *in, double *out, long long n, const PeakPartial *peak) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[n - 1 - i] = in[i] / peak->mx;
+}
+
+// ---- covariance fit reductions -------------------------------------------------------------------
+struct CovParams {
+  const double *map;
+  Dims d;
+  double sx, sy, sz;  // node spacing
+  double thresh;
+  int use_win, x1, x2, y1, y2, z1, z2;  // window [x1,x2) ... when use_win
+  double xe, ye, ze;  // pass 2 only
+};
+
+template <int PASS>
+__global__ void __launch_bounds__(256) k_cov_partial(CovParams p, double *part /* [blocks][8] */) {
+  double a[7] = {0, 0, 0, 0, 0, 0, 0};
+  const long long n = (long long)p.d.nx * p.d.ny * p.d.nz;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double w = p.map[i];
+    if (!(w > p.thresh)) continue;  // also drops NaN
+    const int iz = (int)(i % p.d.nz), iy = (int)((i / p.d.nz) % p.d.ny), ix = (int)(i / ((long long)p.d.nz * p.d.ny));
+    if (p.use_win && (ix < p.x1 || ix >= p.x2 || iy < p.y1 || iy >= p.y2 || iz < p.z1 || iz >= p.z2)) continue;
+    const double x = ix * p.sx, y = iy * p.sy, z = iz * p.sz;
+    if (PASS == 1) {
+      a[0] += w; a[1] += w * x; a[2] += w * y; a[3] += w * z;
+    } else {
+      const double dx = x - p.xe, dy = y - p.ye, dz = z - p.ze;
+      a[0] += w * dx * dx; a[1] += w * dy * dy; a[2] += w * dz * dz;
+      a[3] += w * dx * dy; a[4] += w * dx * dz; a[5] += w * dy * dz;
+    }
+  }
+  __shared__ double s[7][256];
+  for (int k = 0; k < 7; ++k) s[k][threadIdx.x] = a[k];
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o)
+      for (int k = 0; k < 7; ++k) s[k][threadIdx.x] += s[k][threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+    for (int k = 0; k < 7; ++k) part[(size_t)blockIdx.x * 8 + k] = s[k][0];
+}
+
+__global__ void k_cov_final(const double *part, int n_parts, double *out /* [8] */) {
+  double a[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int q = 0; q < n_parts; ++q)
+    for (int k = 0; k < 7; ++k) a[k] += part[(size_t)q * 8 + k];
+  for (int k = 0; k < 7; ++k) out[k] = a[k];
+}
+
+int gaussian_taps(int n, double sgm, std::vector<double> &w, int &m_lo, int &m_hi) {
+  w.assign(n, 0.0);
+  const double c = (n - 1) / 2.0;
+  m_lo = n;
+  m_hi = -1;
+  for (int m = 0; m < n; ++m) {
+    const double r = m - c;
+    const double v = exp(-(r * r) / (2.0 * sgm * sgm));  // util.py:110-114
+    w[m] = v;
+    if (v != 0.0) {
+      if (m < m_lo) m_lo = m;
+      m_hi = m;
+    }
+  }
+  return QMB_OK;
+}
+
+struct MapScratch {
+  double *a = nullptr, *b = nullptr, *c = nullptr, *w = nullptr;
+  PeakPartial *part = nullptr, *peak = nullptr;
+  ~MapScratch() {
+    if (a) cudaFree(a);
+    if (b) cudaFree(b);
+    if (c) cudaFree(c);
+    if (w) cudaFree(w);
+    if (part) cudaFree(part);
+    if (peak) cudaFree(peak);
+  }
+};
+
+constexpr int RED_BLOCKS = 592;
+
+int peak_of(qmb_ctx *ctx, const double *d_map, long long n, PeakPartial *d_part, PeakPartial *d_peak) {
+  k_peak_partial<<<RED_BLOCKS, 256, 0, ctx->stream>>>(d_map, n, d_part);
+  k_peak_final<<<1, 1, 0, ctx->stream>>>(d_part, RED_BLOCKS, d_peak);
+  ctx->launches += 2;
+  QMB_CUDA(cudaGetLastError());
+  return QMB_OK;
+}
+
+// three separable passes: src -> dst (tmp is clobbered)
+int conv3(qmb_ctx *ctx, const double *src, double *dst, double *tmp, Dims d, const double *d_w, const int *lo,
+          const int *hi, const int *off) {
+  const long long n = (long long)d.nx * d.ny * d.nz;
+  const int blocks = (int)((n + 255) / 256);
+  const int ns[3] = {d.nx, d.ny, d.nz};
+  const double *in = src;
+  double *bufs[3] = {dst, tmp, dst};
+  for (int axis = 0; axis < 3; ++axis) {
+    k_conv_axis<<<blocks, 256, 0, ctx->stream>>>(in, bufs[axis], d, axis, d_w + off[axis], lo[axis], hi[axis],
+                                                 (ns[axis] - 1) / 2);
+    ctx->launches++;
+    in = bufs[axis];
+  }
+  QMB_CUDA(cudaGetLastError());
+  return QMB_OK;
+}
+
+}  // namespace
+
+// QuakeScan._gaufilt3d (scan.py:1008-1043)
+extern "C" int qmb_gaufilt3d(qmb_ctx_t ctx, const double *map3d, int32_t nx, int32_t ny, int32_t nz, double sgm,
+                             double *smoothed) {
+  if (!ctx || !map3d || !smoothed) QMB_FAIL(QMB_ERR_ARG, "null argument");
+  if (nx <= 0 || ny <= 0 || nz <= 0 || !(sgm > 0)) QMB_FAIL(QMB_ERR_ARG, "bad map shape or sigma");
+  QMB_CUDA(cudaSetDevice(ctx->device));
+  const Dims d = {nx, ny, nz};
+  const long long n = (long long)nx * ny * nz;
+  MapScratch s;
+  QMB_CUDA(cudaMalloc((void **)&s.a, n * sizeof(double)));
+  QMB_CUDA(cudaMalloc((void **)&s.b, n * sizeof(double)));
+  QMB_CUDA(cudaMalloc((void **)&s.part, RED_BLOCKS * sizeof(PeakPartial)));
+  QMB_CUDA(cudaMalloc((void **)&s.peak, sizeof(PeakPartial)));
+  std::vector<double> w, wa;
+  int lo[3], hi[3], off[3];
+  const int ns[3] = {nx, ny, nz};
+  for (int a = 0; a < 3; ++a) {
+    gaussian_taps(ns[a], sgm, w, lo[a], hi[a]);
+    off[a] = (int)wa.size();
+    wa.insert(wa.end(), w.begin(), w.end());
+  }
+  QMB_CUDA(cudaMalloc((void **)&s.w, wa.size() * sizeof(double)));
+  QMB_CUDA(cudaMemcpyAsync(s.w, wa.data(), wa.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  QMB_CUDA(cudaMemcpyAsync(s.a, map3d, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  const int blocks = (int)((n + 255) / 256);
+  QMB_CUDA(cudaMalloc((void **)&s.c, n * sizeof(double)));
+  double *tmp = s.c;
+  int rc = QMB_OK;
+  for (int rep = 0; rep < 2 && rc == QMB_OK; ++rep) {
+    // a -> (conv) -> b ; b -> (mirror, / max) -> a
+    rc = conv3(ctx, s.a, s.b, tmp, d, s.w, lo, hi, off);
+    if (rc == QMB_OK) rc = peak_of(ctx, s.b, n, s.part, s.peak);
+    if (rc == QMB_OK) {
+      k_mirror_scale<<<blocks, 256, 0, ctx->stream>>>(s.b, s.a, n, s.peak);
+      ctx->launches++;
+    }
+  }
+  cudaError_t e = cudaGetLastError();
+  if (rc == QMB_OK && e == cudaSuccess)
+    e = cudaMemcpyAsync(smoothed, s.a, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (rc == QMB_OK && e != cudaSuccess) {
+    qmb_set_error("qmb_gaufilt3d: %s", cudaGetErrorString(e));
+    rc = QMB_ERR_CUDA;
+  }
+  return rc;
+}
+
+// nanargmax (first), nanmax, nanmean of a map (scan.py:869,878,972)
+extern "C" int qmb_map3d_peak(qmb_ctx_t ctx, const double *map3d, int64_t n, int64_t *argmax, double *maxval,
+                              double *mean) {
+  if (!ctx || !map3d || n <= 0) QMB_FAIL(QMB_ERR_ARG, "bad argument");
+  QMB_CUDA(cudaSetDevice(ctx->device));
+  MapScratch s;
+  QMB_CUDA(cudaMalloc((void **)&s.a, n * sizeof(double)));
+  QMB_CUDA(cudaMalloc((void **)&s.part, RED_BLOCKS * sizeof(PeakPartial)));
+  QMB_CUDA(cudaMalloc((void **)&s.peak, sizeof(PeakPartial)));
+  QMB_CUDA(cudaMemcpyAsync(s.a, map3d, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  QMB_TRY(peak_of(ctx, s.a, n, s.part, s.peak));
+  PeakPartial h;
+  QMB_CUDA(cudaMemcpyAsync(&h, s.peak, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  QMB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (argmax) *argmax = h.idx;
+  if (maxval) *maxval = h.mx;
+  if (mean) *mean = h.cnt > 0 ? h.sum / (double)h.cnt : NAN;
+  return QMB_OK;
+}
+
+// reductions of QuakeScan._covfit3d (scan.py:939-1005).  out[0..2] = expectation (xe, ye, ze) in
+// grid units * spacing (relative to the grid origin), out[3..11] = 3x3 covariance matrix (row major).
+// win <= 0: whole grid; else nodes within +-(win-1)//2 of the maximum (scan.py:1045-1070).
+extern "C" int qmb_covfit3d(qmb_ctx_t ctx, const double *map3d, int32_t nx, int32_t ny, int32_t nz,
+                            const double *spacing, double thresh, int32_t win, double *out12) {
+  if (!ctx || !map3d || !spacing || !out12) QMB_FAIL(QMB_ERR_ARG, "null argument");
+  if (nx <= 0 || ny <= 0 || nz <= 0) QMB_FAIL(QMB_ERR_ARG, "bad map shape");
+  QMB_CUDA(cudaSetDevice(ctx->device));
+  const long long n = (long long)nx * ny * nz;
+  MapScratch s;
+  double *d_part = nullptr, *d_out = nullptr;
+  QMB_CUDA(cudaMalloc((void **)&s.a, n * sizeof(double)));
+  QMB_CUDA(cudaMalloc((void **)&s.b, (RED_BLOCKS * 8 + 8) * sizeof(double)));
+  QMB_CUDA(cudaMalloc((void **)&s.part, RED_BLOCKS * sizeof(PeakPartial)));
+  QMB_CUDA(cudaMalloc((void **)&s.peak, sizeof(PeakPartial)));
+  d_part = s.b;
+  d_out = s.b + RED_BLOCKS * 8;
+  QMB_CUDA(cudaMemcpyAsync(s.a, map3d, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CovParams p = {};
+  p.map = s.a; p.d = {nx, ny, nz}; p.sx = spacing[0]; p.sy = spacing[1]; p.sz = spacing[2]; p.thresh = thresh;
+  if (win > 0) {
+    QMB_TRY(peak_of(ctx, s.a, n, s.part, s.peak));
+    PeakPartial h;
+    QMB_CUDA(cudaMemcpyAsync(&h, s.peak, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    QMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h.idx < 0) QMB_FAIL(QMB_ERR_ARG, "map has no finite value");
+    const int iz = (int)(h.idx % nz), iy = (int)((h.idx / nz) % ny), ix = (int)(h.idx / ((long long)nz * ny));
+    const int w2 = (win - 1) / 2;
+    auto clip = [](int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); };
+    p.use_win = 1;
+    p.x1 = clip(ix - w2, nx); p.x2 = clip(ix + w2 + 1, nx);
+    p.y1 = clip(iy - w2, ny); p.y2 = clip(iy + w2 + 1, ny);
+    p.z1 = clip(iz - w2, nz); p.z2 = clip(iz + w2 + 1, nz);
+  }
+  double h1[8], h2[8];
+  k_cov_partial<1><<<RED_BLOCKS, 256, 0, ctx->stream>>>(p, d_part);
+  k_cov_final<<<1, 1, 0, ctx->stream>>>(d_part, RED_BLOCKS, d_out);
+  ctx->launches += 2;
+  QMB_CUDA(cudaGetLastError());
+  QMB_CUDA(cudaMemcpyAsync(h1, d_out, 7 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  QMB_CUDA(cudaStreamSynchronize(ctx->stream));
+  const double ssw = h1[0];
+  p.xe = h1[1] / ssw; p.ye = h1[2] / ssw; p.ze = h1[3] / ssw;
+  k_cov_partial<2><<<RED_BLOCKS, 256, 0, ctx->stream>>>(p, d_part);
+  k_cov_final<<<1, 1, 0, ctx->stream>>>(d_part, RED_BLOCKS, d_out);
+  ctx->launches += 2;
+  QMB_CUDA(cudaGetLastError());
+  QMB_CUDA(cudaMemcpyAsync(h2, d_out, 7 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  QMB_CUDA(cudaStreamSynchronize(ctx->stream));
+  out12[0] = p.xe; out12[1] = p.ye; out12[2] = p.ze;
+  const double cxx = h2[0] / ssw, cyy = h2[1] / ssw, czz = h2[2] / ssw, cxy = h2[3] / ssw, cxz = h2[4] / ssw,
+               cyz = h2[5] / ssw;
+  const double cov[9] = {cxx, cxy, cxz, cxy, cyy, cyz, cxz, cyz, czz};
+  for (int k = 0; k < 9; ++k) out12[3 + k] = cov[k];
+  return QMB_OK;
+}

@@ -157,7 +157,8 @@ class QuakeScan:
             if owned:
                 dev.free()
 
-    def compute_locate(self, data, marginal_window: float | None = None, return_map4d: bool = False):
+    def compute_locate(self, data, marginal_window: float | None = None, return_map4d: bool = False,
+                       fit_location: bool = False):
         """
         Fast locate: the max-coalescence traces over the whole span, then only the marginal
         window around the peak (io/event.py:421-439) is re-migrated on the device.
@@ -188,6 +189,10 @@ class QuakeScan:
             else:  # degenerate single-row window: the reference slices an empty map
                 out["coa_map"] = np.zeros(dlut.shape[:-1])
                 out["map4d"] = np.zeros(dlut.shape[:-1] + (0,)) if return_map4d else None
+            if fit_location and i1 > i0:
+                # _calculate_location (scan.py:696-733): spline / Gaussian / covariance estimates
+                from .locate import calculate_location
+                out["location"] = calculate_location(out["coa_map"], self.lut, self.engine)
             return out
         finally:
             if owned:

@@ -91,7 +91,7 @@ def test_compute_detect_and_locate(position):
     np.testing.assert_allclose(map4d, r_map4d, rtol=1e-5)
 
     # fast locate: marginal window only (event.py:421-439, scan.py:720-721)
-    out = scan.compute_locate(data, return_map4d=True)
+    out = scan.compute_locate(data, return_map4d=True, fit_location=True)
     i0, i1, imax = marginal_window_indices(r_max, 1.0, cfg.sampling_rate)
     assert out["window"] == (i0, i1) and out["peak_sample"] == imax
     want = r_map4d[..., i0:i1]
@@ -99,6 +99,17 @@ def test_compute_detect_and_locate(position):
     coa_map = out["coa_map"] / np.nanmax(out["coa_map"])
     r_coa_map = want.sum(axis=-1)
     np.testing.assert_allclose(coa_map, r_coa_map / np.nanmax(r_coa_map), rtol=1e-5)
+    # location estimates (scan.py:696-733) against the oracle restatement on the reference map
+    from quakemigrate_b200 import locate
+    r_norm_map = r_coa_map / np.nanmax(r_coa_map)
+    e, cov = O.np_covfit3d(r_norm_map, lut.node_spacing)
+    np.testing.assert_allclose(out["location"]["covariance"][0], lut.ll_corner + e, rtol=1e-6)
+    np.testing.assert_allclose(out["location"]["covariance"][1], np.diag(np.sqrt(np.abs(cov))), rtol=1e-4)
+    r_sm = O.np_gaufilt3d(r_norm_map)
+    r_ijk = np.unravel_index(np.nanargmax(r_sm), r_sm.shape)
+    g_idx, g_sig = locate.gaussian_fit(r_sm, r_ijk, np.nanmean(r_sm))
+    np.testing.assert_allclose(out["location"]["gaussian"][0], lut.index2coord([list(g_idx)])[0], rtol=1e-5)
+    np.testing.assert_allclose(out["location"]["gaussian"][1], g_sig * lut.node_spacing, rtol=1e-3)
     scan.close()
     eng.close()
 
