@@ -151,8 +151,8 @@ void tile_region(const Region &r, int sx, int sy, int sz, std::vector<int> &boxe
 
 }  // namespace
 
-int qmb_lut_build(qmb_ctx *ctx, qmb_lut *L, const int32_t *d_raw, const QmbServeSource *src) {
-  L->v = QMB_VARIANTS[ctx->variant];
+static int lut_build_variant(qmb_ctx *ctx, qmb_lut *L, const int32_t *d_raw, const QmbServeSource *src, int variant) {
+  L->v = QMB_VARIANTS[variant];
   L->tx = L->v.tx;
   L->ty = L->v.ty;
   L->tz = L->v.tz;
@@ -218,4 +218,32 @@ int qmb_lut_build(qmb_ctx *ctx, qmb_lut *L, const int32_t *d_raw, const QmbServe
              "travel-time range inside one %dx%dx%d node tile exceeds 65535 samples", L->tx, L->ty,
              L->tz);
   return QMB_OK;
+}
+
+// Pipeline stages the scan kernel would get for this table (mirrors scan_setup in qmb_scan.cu).
+int qmb_lut_stage_count(const qmb_lut *L) {
+  const int TT = 32 * L->v.K;
+  const int RS = ((L->max_span + TT + 3) & ~3) + 4;
+  int stage_bytes = L->chunk_rows * RS * 4 + L->chunk_rows * L->NB * 2 + L->NB * 4;
+  stage_bytes = (stage_bytes + 127) & ~127;
+  return (QMB_SMEM_BUDGET - 1024) / (stage_bytes + 16);
+}
+
+// Tile with the context's variant; if the travel-time range inside a tile is so wide that fewer
+// than three pipeline stages fit in shared memory, fall back to variants with fewer rows per stage
+// (4) and then smaller node tiles (6) before giving up.
+int qmb_lut_build(qmb_ctx *ctx, qmb_lut *L, const int32_t *d_raw, const QmbServeSource *src) {
+  const int order[3] = {ctx->variant, 4, 6};
+  int rc = QMB_OK;
+  for (int k = 0; k < 3; ++k) {
+    if (k > 0 && order[k] == order[k - 1]) continue;
+    rc = lut_build_variant(ctx, L, d_raw, src, order[k]);
+    if (rc != QMB_OK) return rc;
+    const int stages = qmb_lut_stage_count(L);
+    if (stages >= 3 || (k == 2 && stages >= 2)) return QMB_OK;
+  }
+  if (qmb_lut_stage_count(L) >= 2) return QMB_OK;
+  QMB_FAIL(QMB_ERR_UNSUPPORTED,
+           "travel-time range inside one node tile (%d samples) is too wide for the shared-memory pipeline",
+           L->max_span);
 }

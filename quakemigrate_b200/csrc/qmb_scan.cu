@@ -366,22 +366,26 @@ __global__ void __launch_bounds__(256) k_merge(const float *pm1, const float *pm
                                                const double *psum, int n_parts, long long stride,
                                                long long stride_sum, long long n, float *gm1, float *gm2, float *gm3,
                                                uint32_t *gi1, uint32_t *gi2, double *gsum) {
+  // blockIdx.y selects a group of parts; group g writes its fold at offset g * n (two-stage merge)
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
+  const int per = (n_parts + gridDim.y - 1) / gridDim.y;
+  const int q0 = blockIdx.y * per, q1 = min(n_parts, q0 + per);
   Top3 a;
   a.m1 = a.m2 = a.m3 = __int_as_float(0xff800000);
   a.i1 = a.i2 = 0xFFFFFFFFu;
   double s = 0.0;
-  for (int q = 0; q < n_parts; ++q) {
+  for (int q = q0; q < q1; ++q) {
     const size_t o = (size_t)q * stride + t;
     top3_insert(a, pm1[o], pi1[o]);
     top3_insert(a, pm2[o], pi2[o]);
     a.m3 = fmaxf(a.m3, pm3[o]);
     s += psum[(size_t)q * stride_sum + t];
   }
-  gm1[t] = a.m1; gm2[t] = a.m2; gm3[t] = a.m3;
-  gi1[t] = a.i1; gi2[t] = a.i2;
-  gsum[t] = s;
+  const size_t w = (size_t)blockIdx.y * n + t;
+  gm1[w] = a.m1; gm2[w] = a.m2; gm3[w] = a.m3;
+  gi1[w] = a.i1; gi2[w] = a.i2;
+  gsum[w] = s;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -686,8 +690,8 @@ int qmb_scan_run(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, int32_t fsmp, int32_t 
   p.pm1 = ctx->pm1.p; p.pm2 = ctx->pm2.p; p.pm3 = ctx->pm3.p;
   p.pi1 = ctx->pi1.p; p.pi2 = ctx->pi2.p; p.psum = ctx->psum.p;
   const size_t Tp = (size_t)p.Tpad;
-  QMB_TRY(ctx->gm1.ensure(Tp)); QMB_TRY(ctx->gm2.ensure(Tp)); QMB_TRY(ctx->gm3.ensure(Tp));
-  QMB_TRY(ctx->gi1.ensure(Tp)); QMB_TRY(ctx->gi2.ensure(Tp)); QMB_TRY(ctx->gsum.ensure(Tp));
+  QMB_TRY(ctx->gm1.ensure(Tp * 33)); QMB_TRY(ctx->gm2.ensure(Tp * 33)); QMB_TRY(ctx->gm3.ensure(Tp * 33));
+  QMB_TRY(ctx->gi1.ensure(Tp * 33)); QMB_TRY(ctx->gi2.ensure(Tp * 33)); QMB_TRY(ctx->gsum.ensure(Tp * 33));
   QMB_TRY(ctx->ex1.ensure(Tp)); QMB_TRY(ctx->ex2.ensure(Tp));
   QMB_TRY(ctx->r_max.ensure((size_t)T)); QMB_TRY(ctx->r_norm.ensure((size_t)T)); QMB_TRY(ctx->r_idx.ensure((size_t)T));
   const int slow_cap = (int)T;
@@ -709,9 +713,26 @@ int qmb_scan_run(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, int32_t fsmp, int32_t 
 
   // ---- merge partials (local), then across ranks ----------------------------------------------
   const int mb = (int)((p.Tpad + 255) / 256);
-  k_merge<<<mb, 256, 0, ctx->stream>>>(p.pm1, p.pm2, p.pm3, p.pi1, p.pi2, p.psum, R * L->v.W,
-                                       p.Tpad, p.Tpad, p.Tpad, ctx->gm1.p, ctx->gm2.p, ctx->gm3.p, ctx->gi1.p,
-                                       ctx->gi2.p, ctx->gsum.p);
+  {
+    // many parts (short scans over big grids): fold in G groups first, then fold the groups.
+    // The group results live behind the final arrays (offset Tpad).
+    const int n_parts = R * L->v.W;
+    const int G = n_parts >= 256 ? 32 : 1;
+    if (G > 1) {
+      k_merge<<<dim3(mb, G), 256, 0, ctx->stream>>>(p.pm1, p.pm2, p.pm3, p.pi1, p.pi2, p.psum, n_parts, p.Tpad,
+                                                    p.Tpad, p.Tpad, ctx->gm1.p + Tp, ctx->gm2.p + Tp,
+                                                    ctx->gm3.p + Tp, ctx->gi1.p + Tp, ctx->gi2.p + Tp,
+                                                    ctx->gsum.p + Tp);
+      k_merge<<<mb, 256, 0, ctx->stream>>>(ctx->gm1.p + Tp, ctx->gm2.p + Tp, ctx->gm3.p + Tp, ctx->gi1.p + Tp,
+                                           ctx->gi2.p + Tp, ctx->gsum.p + Tp, G, p.Tpad, p.Tpad, p.Tpad,
+                                           ctx->gm1.p, ctx->gm2.p, ctx->gm3.p, ctx->gi1.p, ctx->gi2.p, ctx->gsum.p);
+      ctx->launches++;
+    } else {
+      k_merge<<<mb, 256, 0, ctx->stream>>>(p.pm1, p.pm2, p.pm3, p.pi1, p.pi2, p.psum, n_parts, p.Tpad, p.Tpad,
+                                           p.Tpad, ctx->gm1.p, ctx->gm2.p, ctx->gm3.p, ctx->gi1.p, ctx->gi2.p,
+                                           ctx->gsum.p);
+    }
+  }
   ctx->launches++;
   QMB_CUDA(cudaGetLastError());
   if (ctx->world > 1) {

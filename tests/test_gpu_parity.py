@@ -101,6 +101,9 @@ def test_onsets_from_waveforms(engine):
     ((9, 8, 10), 16, 300, 0, 64),      # fsmp = 0
     ((13, 4, 4), 33, 513, 7, 31),      # three row chunks, T not multiple of the tile
     ((4, 4, 4), 1, 1, 1, 5),           # single row, single sample
+    ((5, 5, 5), 128, 300, 4, 40),      # BASELINE cfg5 row count (128 rows)
+    ((6, 4, 7), 64, 257, 0, 33),       # BASELINE cfg3 row count
+    ((3, 2, 2), 24, 640, 413, 1000),   # BASELINE cfg1 pads (fsmp 413, lsmp 1000), grid < one tile
 ])
 def test_detect_random(engine_v, grid, S, T, fsmp, lsmp):
     onsets, tau = syn.random_problem(S * 1000 + T, grid, S, T, fsmp, lsmp, neg_frac=0.05)
