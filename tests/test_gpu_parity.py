@@ -199,3 +199,36 @@ def test_locate_window(engine_v):
         np.testing.assert_allclose(coa, m4[..., w0:w1].sum(axis=-1), rtol=RTOL_COA)
     dev.free()
     lut.free()
+
+
+def test_detect_random_shapes(engine):
+    """Seeded sweep over awkward shapes: tiny grids, T < one lane group, S = 1, zero pads."""
+    rng = np.random.default_rng(20260925)
+    for case in range(40):
+        grid = tuple(int(x) for x in rng.integers(1, 10, size=3))
+        S = int(rng.integers(1, 41))
+        T = int(rng.choice([1, 2, 31, 32, 33, 255, 256, 257, int(rng.integers(1, 700))]))
+        fsmp = int(rng.choice([0, 1, 2, 3, int(rng.integers(0, 50))]))
+        lsmp = int(rng.integers(0, 80))
+        onsets, tau = syn.random_problem(1000 + case, grid, S, T, fsmp, lsmp,
+                                         neg_frac=float(rng.choice([0.0, 0.1])),
+                                         floor_frac=float(rng.choice([0.0, 0.3, 0.95])))
+        lut = engine.upload_lut(tau)
+        got = engine.detect(lut, onsets, fsmp, lsmp, S)
+        want = O.find_max_coa(O.migrate(onsets, tau, fsmp, lsmp, S, threads=2), threads=2)
+        assert np.array_equal(got[2], want[2]), (case, grid, S, T, fsmp, lsmp)
+        np.testing.assert_allclose(got[0], want[0], rtol=RTOL_COA_TIGHT, err_msg=str((case, grid, S, T)))
+        np.testing.assert_allclose(got[1], want[1], rtol=RTOL_NORM, err_msg=str((case, grid, S, T)))
+        lut.free()
+
+
+def test_available_differs_from_row_count(engine):
+    """exp(stack / available) uses `available`, not the row count (migratelib.c:62)."""
+    grid, S, T, fsmp, lsmp = (5, 4, 6), 6, 120, 3, 25
+    onsets, tau = syn.random_problem(5, grid, S, T, fsmp, lsmp)
+    lut = engine.upload_lut(tau)
+    for avail in (1, 4, 9):
+        got = engine.detect(lut, onsets, fsmp, lsmp, avail)
+        want = O.find_max_coa(O.migrate(onsets, tau, fsmp, lsmp, avail, threads=2), threads=2)
+        _check_detect(got, want)
+    lut.free()
