@@ -42,7 +42,7 @@ void qmb_set_error(const char *fmt, ...);
 struct QmbVariant {
   int id, W, NPW, K, tx, ty, tz, CR;  // CR = onset rows staged per pipeline stage
 };
-constexpr int QMB_N_VARIANTS = 8;
+constexpr int QMB_N_VARIANTS = 10;
 constexpr QmbVariant QMB_VARIANTS[QMB_N_VARIANTS] = {
     {0, 16, 4, 8, 4, 4, 4, 16},  // 17 warps -> 96 regs/thread
     {1, 16, 8, 4, 4, 4, 8, 16},
@@ -52,6 +52,8 @@ constexpr QmbVariant QMB_VARIANTS[QMB_N_VARIANTS] = {
     {5, 12, 8, 4, 4, 4, 6, 16},
     {6, 8, 4, 8, 4, 4, 2, 16},
     {7, 12, 4, 8, 4, 4, 3, 32},  // as 4, 32 rows per stage: half the stage hand-offs
+    {8, 15, 4, 8, 5, 4, 3, 32},  // 16 warps in all -> still 128 regs/thread, 60-node tiles
+    {9, 15, 4, 8, 5, 4, 3, 16},
 };
 constexpr int QMB_DEFAULT_VARIANT = 7;  // measured best on B200 (scripts/sweep_variants.sh)
 constexpr int QMB_DEFAULT_CHUNK_ROWS = 16;  // onset rows (station x phase) staged per pipeline stage

@@ -572,6 +572,8 @@ int dispatch_scan(qmb_ctx *ctx, const QmbVariant &v, const ScanParams &p, int gr
     case 5: return launch_scan<12, 8, 4, MODE, 16>(ctx, p, grid, smem);
     case 6: return launch_scan<8, 4, 8, MODE, 16>(ctx, p, grid, smem);
     case 7: return launch_scan<12, 4, 8, MODE, 32>(ctx, p, grid, smem);
+    case 8: return launch_scan<15, 4, 8, MODE, 32>(ctx, p, grid, smem);
+    case 9: return launch_scan<15, 4, 8, MODE, 16>(ctx, p, grid, smem);
   }
   QMB_FAIL(QMB_ERR_ARG, "unknown kernel variant %d", v.id);
 }

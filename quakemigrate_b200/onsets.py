@@ -215,8 +215,6 @@ class STALTAOnset(Onset):
         ``(n_available_rows, n_samples)``; ``onset_data.device_onsets`` holds the same rows
         (clip+log applied) on the GPU for the scan.
         """
-        if timespan is not None:
-            raise NotImplementedError("timespan (taper nulling for the picker) is not part of the hot path")
         if self.engine is None:
             from .core import Engine
             self.engine = Engine(0)
@@ -228,6 +226,19 @@ class STALTAOnset(Onset):
             waveforms, [r[2] for r in rows], [r[3] for r in rows], [r[4] for r in rows],
             position=self.position, transform=self.signal_transform,
             min_onset_value=self.min_onset_value, return_onsets=True)
+        if timespan:
+            # _trim_taper_pad (stalta.py:550-584): the tapered pre-/post-pad plus one LTA / STA
+            # window is set to 1 on every channel before the RMS combine; every channel of a row
+            # shares its windows, so RMS(1, .., 1) = 1 >= min_onset_value and nulling the combined
+            # row is identical.  Only the picker asks for this (gaussian.py:142): the device copy
+            # is dropped so that nobody migrates nulled onsets by accident.
+            pre_pad, _ = self.pad(timespan)
+            taper_pad = time2sample(pre_pad - self.pre_pad, self.sampling_rate)
+            for i, (_, _, _, nsta, nlta) in enumerate(rows):
+                onsets[i, : (taper_pad + nlta - 1)] = 1.0
+                onsets[i, -(nsta + taper_pad):] = 1.0
+            dev.free()
+            dev = None
         onsets_dict = {}
         for i, (station, phase, _, _, _) in enumerate(rows):
             onsets_dict.setdefault(station, {})[phase] = onsets[i]

@@ -30,7 +30,7 @@ def engine():
     eng.close()
 
 
-@pytest.fixture(scope="module", params=list(range(8)))
+@pytest.fixture(scope="module", params=list(range(10)))
 def engine_v(request):
     """Every kernel tiling variant (QMB_VARIANTS in csrc/qmb_internal.cuh)."""
     from quakemigrate_b200.core import Engine

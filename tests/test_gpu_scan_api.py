@@ -144,3 +144,25 @@ def test_device_served_table_equals_host_served():
     with pytest.raises(KeyError):
         lut.rows_for({"ST000_X": 1}, index)
     eng.close()
+
+
+def test_onset_timespan_nulls_taper_windows():
+    """STALTAOnset.calculate_onsets(data, timespan): _trim_taper_pad semantics (stalta.py:550-584)."""
+    from quakemigrate_b200.core import Engine
+    from quakemigrate_b200.onsets import STALTAOnset
+    cfg, prob, lut, data = _problem()
+    eng = Engine(0)
+    onset = STALTAOnset(engine=eng, sampling_rate=cfg.sampling_rate,
+                        sta_lta_windows={"P": [cfg.sta, cfg.lta], "S": [cfg.sta, cfg.lta]})
+    onset.post_pad = lut.max_traveltime
+    plain, od = onset.calculate_onsets(data)
+    nulled, od2 = onset.calculate_onsets(data, timespan=8.0)
+    assert od.device_onsets is not None and od2.device_onsets is None
+    pre_pad, _ = onset.pad(8.0)
+    taper = syn.time2sample(pre_pad - onset.pre_pad, cfg.sampling_rate)
+    nsta, nlta = prob.nsta, prob.nlta
+    want = plain.copy()
+    want[:, : taper + nlta - 1] = 1.0
+    want[:, -(nsta + taper):] = 1.0
+    assert np.array_equal(nulled, want)
+    eng.close()
