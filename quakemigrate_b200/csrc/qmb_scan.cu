@@ -6,12 +6,12 @@
 //
 // Work decomposition
 //   item      = (time tile of 32*K samples) x (contiguous range of node tiles)
-//   CTA       = persistent; walks items  blockIdx.x, +gridDim.x, ...
-//   node tile = 16*NPW spatially compact nodes (4x4x4 or 4x4x8), laid out by qmb_lut.cu
-//   stage     = (node tile, chunk of 16 onset rows): the producer warp bulk-copies, per row, the
+//   CTA       = persistent, one per SM; walks items  blockIdx.x, +gridDim.x, ...
+//   node tile = W*NPW spatially compact nodes (default 12*4 = 48: 4x4x3 boxes), laid out by qmb_lut.cu
+//   stage     = (node tile, chunk of CR onset rows): the producer warp bulk-copies, per row, the
 //               window [tmin4, tmin4 + span + 32K) of the float32 log-onset row into shared memory
 //               (cp.async.bulk -> SASS UBLKCP, completion on an mbarrier) plus the tile's uint16
-//               tau offsets; a ring of stages decouples it from the 16 consumer warps.
+//               tau offsets; a ring of stages decouples it from the W consumer warps.
 //   consumer  = warp w owns NPW nodes of the tile; LANES ARE TIME SAMPLES (lane l handles
 //               samples 32k + l), so every shared-memory gather of a shifted onset row is a
 //               contiguous, conflict-free 128-byte wavefront whatever the travel times are, and
@@ -95,7 +95,7 @@ struct ScanParams {
   const float *on32;     // [S][row_stride]
   long long row_stride;  // elements
   long long t_origin;    // index within a row of (tau = 0, sample t' = 0); multiple of 4
-  int S, n_chunks, chunk_rows;
+  int S, n_chunks;       // n_chunks = stages per node tile (rows / CR)
   // LUT tiles
   const uint16_t *tau16;
   const int32_t *tmin;
@@ -106,7 +106,7 @@ struct ScanParams {
   int RS;            // shared row stride (floats), multiple of 4
   int n_stages;
   int stage_bytes;
-  int n_time_tiles, R, tiles_per_item;
+  int n_time_tiles, R;   // items = n_time_tiles x R node ranges (ranges balanced to +-1 tile)
   float scale;       // log2(e) / available
   // per-(item range, warp) partial results, indexed [(r*16 + w) * Tpad + t']
   float *pm1, *pm2, *pm3;
@@ -595,7 +595,6 @@ static int scan_setup(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, long long first, 
   p.T = T;
   p.t_origin = O->front + first - shift;
   p.S = L->S;
-  p.chunk_rows = L->chunk_rows;
   p.n_chunks = L->Spad / L->chunk_rows;
   p.tau16 = L->tau16.p; p.tmin = L->tmin.p; p.span = L->span.p; p.nodeidx = L->nodeidx.p;
   p.n_tiles = L->n_tiles; p.Spad = L->Spad;
@@ -633,7 +632,6 @@ static int scan_setup(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, long long first, 
     const int forced = atoi(env);
     if (forced >= 1 && forced <= std::max(1, L->n_tiles)) R = forced;
   }
-  p.tiles_per_item = (L->n_tiles + R - 1) / R;
   p.R = R;
   p.scale = (float)(1.4426950408889634 / (double)available);
   p.Tpad = (long long)p.n_time_tiles * TT;
