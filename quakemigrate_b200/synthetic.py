@@ -91,6 +91,8 @@ CONFIGS = {
     "cfg3": SynthConfig("cfg3", (201, 201, 101), 64, 360000, "classic", seed=3, n_events=100),
     "cfg4": SynthConfig("cfg4", (151, 151, 151), 48, 30000, "centred", seed=4, n_events=1),
     "cfg5": SynthConfig("cfg5", (301, 301, 151), 128, 600000, "centred", seed=5, n_events=150),
+    # one GPU's x-slab of cfg5 when the grid is sharded over 8 GPUs (38 of 301 x-planes)
+    "cfg5slab": SynthConfig("cfg5slab", (38, 301, 151), 128, 600000, "centred", seed=5, n_events=150),
 }
 
 
