@@ -196,6 +196,13 @@ class Engine:
             _lib.check(self._lib.qmb_ctx_set_variant(self._h, int(variant)))
 
     # -- lifetime ---------------------------------------------------------------------------
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
     def close(self):
         if getattr(self, "_h", None):
             self._lib.qmb_ctx_destroy(self._h)
