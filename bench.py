@@ -301,7 +301,7 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
             "n_nodes": N_global, "n_rows": S, "n_samples": T, "fsmp": prob.fsmp, "lsmp": prob.lsmp,
             "parallelism": f"node-slab x{world}", "cache": "L2 flushed (256 MiB memset) before every timed step",
             "nodes_per_tile": info["nodes_per_tile"], "max_tile_span": info["max_tile_span"],
-            "variant": args.variant,
+            "variant": info["variant"], "duplicate_fraction": round(info["duplicate_fraction"], 4),
             "timing": "sum of per-step CUDA-event times on the launching stream, max over ranks",
         },
         "e2e": {"value": N_global * T / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": int(onsets_lin.nbytes),

@@ -127,6 +127,8 @@ typedef struct {
   int64_t n_nodes_local, n_nodes_global, node_offset;
   int32_t n_rows, max_tau, max_tile_span, n_tiles, nodes_per_tile;
   int64_t device_bytes;
+  double duplicate_fraction; /* neighbouring nodes (inside a warp group) sharing a row's travel time */
+  int32_t variant, reserved; /* kernel tiling variant id actually used (after span fall-back) */
 } qmb_lut_info_t;
 int qmb_lut_info(qmb_lut_t lut, qmb_lut_info_t *info);
 

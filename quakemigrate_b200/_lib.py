@@ -43,7 +43,8 @@ TRANSFORM = {"none": 0, "energy": 1, "abs": 2}
 class LutInfo(ctypes.Structure):
     _fields_ = [("n_nodes_local", c_int64), ("n_nodes_global", c_int64), ("node_offset", c_int64),
                 ("n_rows", c_int32), ("max_tau", c_int32), ("max_tile_span", c_int32),
-                ("n_tiles", c_int32), ("nodes_per_tile", c_int32), ("device_bytes", c_int64)]
+                ("n_tiles", c_int32), ("nodes_per_tile", c_int32), ("device_bytes", c_int64),
+                ("duplicate_fraction", c_double), ("variant", c_int32), ("reserved", c_int32)]
 
 
 class QmbError(RuntimeError):

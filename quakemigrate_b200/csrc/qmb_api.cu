@@ -361,6 +361,7 @@ extern "C" int qmb_lut_info(qmb_lut_t L, qmb_lut_info_t *info) {
   info->n_nodes_local = L->n_local; info->n_nodes_global = L->n_global; info->node_offset = L->node_offset;
   info->n_rows = L->S; info->max_tau = L->max_tau; info->max_tile_span = L->max_span;
   info->n_tiles = L->n_tiles; info->nodes_per_tile = L->NB;
+  info->duplicate_fraction = L->dup_frac; info->variant = L->v.id; info->reserved = 0;
   info->device_bytes = (int64_t)(L->tau16.bytes() + L->tmin.bytes() + L->span.bytes() + L->nodeidx.bytes() +
                                   L->boxes.bytes() + L->slotmap.bytes());
   return QMB_OK;

@@ -10,6 +10,9 @@
 // so that one 16-byte-aligned bulk copy of  [tmin4, tmin4 + span + time_tile)  of the onset row
 // serves every node of the tile.  The clamp of negative travel times (migratelib.c:55) is
 // applied here, once.
+#include <stdlib.h>
+#include <string.h>
+
 #include "qmb_internal.cuh"
 
 namespace {
@@ -33,6 +36,8 @@ struct LutTileParams {
   uint16_t *span;
   uint32_t *nodeidx;
   int *stats;  // [0] max tau, [1] max span, [2] overflow flag
+  int NPW;     // nodes per consumer warp (for the duplicate statistic)
+  unsigned long long *dup;  // [0] same-offset neighbours inside a warp's node group, [1] pairs examined
 };
 
 __global__ void __launch_bounds__(LT_THREADS) k_lut_tile(LutTileParams p) {
@@ -62,6 +67,7 @@ __global__ void __launch_bounds__(LT_THREADS) k_lut_tile(LutTileParams p) {
   __syncthreads();
 
   int my_max_tau = 0, my_max_span = 0, overflow = 0;
+  unsigned int my_dup = 0, my_pairs = 0;
   for (int s0 = 0; s0 < p.Spad; s0 += LT_ROWS) {
     // gather: one warp per node slot, lanes over rows (coalesced 128-byte reads of the raw table)
     for (int q = warp; q < p.NB; q += NWARPS) {
@@ -91,8 +97,13 @@ __global__ void __launch_bounds__(LT_THREADS) k_lut_tile(LutTileParams p) {
       const int base = mn & ~3;
       const int sp = mx - base;
       if (sp > 65535) overflow = 1;
-      for (int q = lane; q < p.NB; q += 32)
+      for (int q = lane; q < p.NB; q += 32) {
         p.tau16[((size_t)j * p.Spad + s) * p.NB + q] = (uint16_t)min(s_tau[r][q] - base, 65535);
+        if (s < p.S && (q % p.NPW) != 0) {  // neighbour inside the same consumer warp's node group
+          ++my_pairs;
+          if (s_tau[r][q] == s_tau[r][q - 1]) ++my_dup;
+        }
+      }
       if (lane == 0) {
         p.tmin[(size_t)j * p.Spad + s] = base;
         p.span[(size_t)j * p.Spad + s] = (uint16_t)min(sp, 65535);
@@ -102,10 +113,16 @@ __global__ void __launch_bounds__(LT_THREADS) k_lut_tile(LutTileParams p) {
     }
     __syncthreads();
   }
+  for (int o = 16; o > 0; o >>= 1) {
+    my_dup += __shfl_xor_sync(0xffffffffu, my_dup, o);
+    my_pairs += __shfl_xor_sync(0xffffffffu, my_pairs, o);
+  }
   if (lane == 0) {
     atomicMax(&p.stats[0], my_max_tau);
     atomicMax(&p.stats[1], my_max_span);
     if (overflow) atomicMax(&p.stats[2], 1);
+    atomicAdd(&p.dup[0], (unsigned long long)my_dup);
+    atomicAdd(&p.dup[1], (unsigned long long)my_pairs);
   }
 }
 
@@ -187,9 +204,9 @@ static int lut_build_variant(qmb_ctx *ctx, qmb_lut *L, const int32_t *d_raw, con
   QMB_TRY(L->span.ensure((size_t)L->n_tiles * L->Spad));
   QMB_TRY(L->nodeidx.ensure((size_t)L->n_tiles * L->NB));
 
-  int *d_stats = nullptr;
-  QMB_CUDA(cudaMalloc((void **)&d_stats, 4 * sizeof(int)));
-  QMB_CUDA(cudaMemsetAsync(d_stats, 0, 4 * sizeof(int), ctx->stream));
+  int *d_stats = nullptr;  // 4 ints followed (8-byte aligned) by 2 64-bit counters
+  QMB_CUDA(cudaMalloc((void **)&d_stats, 8 * sizeof(int)));
+  QMB_CUDA(cudaMemsetAsync(d_stats, 0, 8 * sizeof(int), ctx->stream));
 
   LutTileParams p = {};
   p.raw = d_raw;
@@ -204,15 +221,22 @@ static int lut_build_variant(qmb_ctx *ctx, qmb_lut *L, const int32_t *d_raw, con
   p.n_valid = L->n_local;
   p.tau16 = L->tau16.p; p.tmin = L->tmin.p; p.span = L->span.p; p.nodeidx = L->nodeidx.p;
   p.stats = d_stats;
+  p.NPW = L->v.NPW;
+  p.dup = (unsigned long long *)(d_stats + 4);
   k_lut_tile<<<L->n_tiles, LT_THREADS, 0, ctx->stream>>>(p);
   ctx->launches++;
   QMB_CUDA(cudaGetLastError());
-  int h_stats[4] = {0, 0, 0, 0};
-  QMB_CUDA(cudaMemcpyAsync(h_stats, d_stats, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  int h_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  QMB_CUDA(cudaMemcpyAsync(h_stats, d_stats, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   QMB_CUDA(cudaStreamSynchronize(ctx->stream));  // also: `boxes` (host vector) was read by the H2D copy
   cudaFree(d_stats);
   L->max_tau = h_stats[0];
   L->max_span = h_stats[1];
+  {
+    unsigned long long d[2];
+    memcpy(d, h_stats + 4, sizeof(d));
+    L->dup_frac = d[1] ? (double)d[0] / (double)d[1] : 0.0;
+  }
   if (h_stats[2])
     QMB_FAIL(QMB_ERR_UNSUPPORTED,
              "travel-time range inside one %dx%dx%d node tile exceeds 65535 samples", L->tx, L->ty,

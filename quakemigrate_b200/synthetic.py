@@ -91,6 +91,11 @@ CONFIGS = {
     "cfg3": SynthConfig("cfg3", (201, 201, 101), 64, 360000, "classic", seed=3, n_events=100),
     "cfg4": SynthConfig("cfg4", (151, 151, 151), 48, 30000, "centred", seed=4, n_events=1),
     "cfg5": SynthConfig("cfg5", (301, 301, 151), 128, 600000, "centred", seed=5, n_events=150),
+    # the Iceland example geometry scanned at 50 Hz (tests/test_benchmarks.py serves the LUT at 50 Hz):
+    # 25 m nodes are ~0.35 samples apart, so most neighbouring nodes share travel-time offsets
+    "cfg1fine": SynthConfig("cfg1fine", (71, 64, 57), 24, 30000, "classic", sampling_rate=50,
+                            node_spacing_km=0.025, vp=3.6, vs=3.6 / 1.9, sta=0.05, lta=0.5,
+                            seed=1, n_events=10),
     # one GPU's x-slab of cfg5 when the grid is sharded over 8 GPUs (38 of 301 x-planes)
     "cfg5slab": SynthConfig("cfg5slab", (38, 301, 151), 128, 600000, "centred", seed=5, n_events=150),
 }

@@ -232,3 +232,16 @@ def test_available_differs_from_row_count(engine):
         want = O.find_max_coa(O.migrate(onsets, tau, fsmp, lsmp, avail, threads=2), threads=2)
         _check_detect(got, want)
     lut.free()
+
+
+def test_fine_grid_with_many_shared_offsets(engine):
+    """Fine grid / low sampling rate: most neighbouring nodes share travel-time offsets."""
+    cfg = syn.CONFIGS["cfg1fine"].scaled(grid=(23, 20, 19), n_samples=700, n_rows=8)
+    prob = syn.make_problem(cfg)
+    onsets = syn.onsets_from_waveforms(prob, lambda x, a, b: O.overlapping_sta_lta(x, a, b))
+    lut = engine.upload_lut(prob.traveltimes)
+    assert lut.info()["duplicate_fraction"] > 0.3
+    got = engine.detect(lut, onsets, prob.fsmp, prob.lsmp, cfg.n_rows)
+    want = O.detect_fused(onsets, prob.traveltimes, prob.fsmp, prob.lsmp, cfg.n_rows, threads=4)
+    _check_detect(got, want)
+    lut.free()
