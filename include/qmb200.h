@@ -201,6 +201,14 @@ int qmb_map3d_peak(qmb_ctx_t ctx, const double *map3d, int64_t n, int64_t *argma
 int qmb_covfit3d(qmb_ctx_t ctx, const double *map3d, int32_t nx, int32_t ny, int32_t nz,
                  const double *spacing, double thresh, int32_t win, double *out12);
 
+/* Micro-benchmark of the pipe that bounds the scan kernel: sustained fp32 gather-adds per second
+ * of conflict-free LDS.32 + FADD streams (13 warps per SM, like k_scan).  Used by bench.py to
+ * report the scan against a MEASURED shared-memory ceiling next to the nominal 32/clk/SM. */
+int qmb_microbench_smem_pipe(qmb_ctx_t ctx, int32_t iters, double *gather_adds_per_s);
+/* exploratory form: vec = floats per lane per load (1, 2, 4), warps per SM in [1, 32] */
+int qmb_microbench_smem_pipe_ex(qmb_ctx_t ctx, int32_t iters, int32_t vec, int32_t warps,
+                                double *gather_adds_per_s);
+
 #ifdef __cplusplus
 }
 #endif

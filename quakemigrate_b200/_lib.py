@@ -104,6 +104,8 @@ SIGNATURES = {
     "qmb_gaufilt3d": (ctypes.c_int, [c_void_p, c_dPt, c_int32, c_int32, c_int32, c_double, c_dPt]),
     "qmb_map3d_peak": (ctypes.c_int, [c_void_p, c_dPt, c_int64, ctypes.POINTER(c_int64),
                                       ctypes.POINTER(c_double), ctypes.POINTER(c_double)]),
+    "qmb_microbench_smem_pipe": (ctypes.c_int, [c_void_p, c_int32, ctypes.POINTER(c_double)]),
+    "qmb_microbench_smem_pipe_ex": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_int32, ctypes.POINTER(c_double)]),
     "qmb_covfit3d": (ctypes.c_int, [c_void_p, c_dPt, c_int32, c_int32, c_int32, c_dPt, c_double, c_int32,
                                     c_dPt]),
 }

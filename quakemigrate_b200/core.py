@@ -223,6 +223,12 @@ class Engine:
         _lib.check(self._lib.qmb_ctx_launch_count(self._h, ctypes.byref(n)))
         return n.value
 
+    def smem_pipe_peak(self, iters: int = 20000) -> float:
+        """Measured ceiling of the shared-memory pipe: LDS.32 + FADD gather-adds per second."""
+        out = ctypes.c_double(0.0)
+        _lib.check(self._lib.qmb_microbench_smem_pipe(self._h, int(iters), ctypes.byref(out)))
+        return out.value
+
     def flush_l2(self):
         """Evict L2 (benchmark hygiene between timed iterations)."""
         _lib.check(self._lib.qmb_ctx_flush_l2(self._h))

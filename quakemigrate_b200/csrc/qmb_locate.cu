@@ -329,3 +329,91 @@ extern "C" int qmb_covfit3d(qmb_ctx_t ctx, const double *map3d, int32_t nx, int3
   for (int k = 0; k < 9; ++k) out12[3 + k] = cov[k];
   return QMB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// micro-benchmark: the ceiling of the pipe that bounds k_scan.  Each warp streams conflict-free
+// 128-byte wavefronts from shared memory into independent fp32 accumulators -- the scan kernel's
+// inner loop with everything else removed (no staging, no offsets, no epilogue).  Measured on
+// B200 (scripts/smem_pipe_sweep.py): 99.5 % of the nominal 32 gather-adds/clk/SM with 12, 16, 24
+// or 32 warps per SM for LDS.32/64/128 alike; 91 % with 13 warps (one scheduler carries 4).
+// ---------------------------------------------------------------------------------------------
+namespace {
+// VEC floats per lane per load (1: LDS.32, 2: LDS.64, 4: LDS.128), any warp count
+template <int VEC, int NV>
+__global__ void k_lds_peak_vec(float *out, int iters) {
+  extern __shared__ float sm[];
+  const int n_words = 32 * 1024;
+  for (int i = threadIdx.x; i < n_words; i += blockDim.x) sm[i] = (float)(i & 7) * 0.125f;
+  __syncthreads();
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(sm);
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float acc[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) acc[j] = 0.f;
+  uint32_t off = (warp * 1024u) & (n_words / 2 - 1);
+#pragma unroll 2
+  for (int it = 0; it < iters; ++it) {
+    const uint32_t a = base + ((off + lane * VEC) << 2);
+    float v[NV];
+#pragma unroll
+    for (int j = 0; j < NV / VEC; ++j) {
+      const uint32_t aj = a + 128u * VEC * j;
+      if constexpr (VEC == 1) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[j]) : "r"(aj));
+      if constexpr (VEC == 2)
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[2 * j]), "=f"(v[2 * j + 1]) : "r"(aj));
+      if constexpr (VEC == 4)
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v[4 * j]), "=f"(v[4 * j + 1]), "=f"(v[4 * j + 2]), "=f"(v[4 * j + 3])
+                     : "r"(aj));
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) acc[j] += v[j];
+    off += 1028u;  // multiple of 4: keeps vector loads aligned
+    if (off >= (uint32_t)(n_words - 32 * NV - 128)) off -= (uint32_t)(n_words - 32 * NV - 128) & ~3u;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) s += acc[j];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <int VEC, int NV>
+int run_vec(qmb_ctx *ctx, int warps, int iters, float *d_out, float *ms) {
+  const size_t smem = 128 * 1024;
+  QMB_CUDA(cudaFuncSetAttribute(k_lds_peak_vec<VEC, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_lds_peak_vec<VEC, NV><<<ctx->sm_count, warps * 32, smem, ctx->stream>>>(d_out, iters / 8 + 1);
+  QMB_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+  k_lds_peak_vec<VEC, NV><<<ctx->sm_count, warps * 32, smem, ctx->stream>>>(d_out, iters);
+  QMB_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+  ctx->launches += 2;
+  QMB_CUDA(cudaStreamSynchronize(ctx->stream));
+  QMB_CUDA(cudaEventElapsedTime(ms, ctx->ev[0], ctx->ev[1]));
+  return QMB_OK;
+}
+}  // namespace
+
+// vec in {1,2,4}, warps in [1,32]; 32 (warps <= 16) or 16 (more warps) values per lane per iteration
+extern "C" int qmb_microbench_smem_pipe_ex(qmb_ctx_t ctx, int32_t iters, int32_t vec, int32_t warps,
+                                           double *gather_adds_per_s) {
+  if (!ctx || !gather_adds_per_s || iters <= 0 || warps < 1 || warps > 32) QMB_FAIL(QMB_ERR_ARG, "bad argument");
+  QMB_CUDA(cudaSetDevice(ctx->device));
+  float *d_out = nullptr;
+  QMB_CUDA(cudaMalloc((void **)&d_out, (size_t)ctx->sm_count * 1024 * sizeof(float)));
+  float ms = 0.f;
+  int rc = QMB_ERR_ARG;
+  const bool big = warps <= 16;
+  if (vec == 1) rc = big ? run_vec<1, 32>(ctx, warps, iters, d_out, &ms) : run_vec<1, 16>(ctx, warps, iters, d_out, &ms);
+  else if (vec == 2) rc = big ? run_vec<2, 32>(ctx, warps, iters, d_out, &ms) : run_vec<2, 16>(ctx, warps, iters, d_out, &ms);
+  else if (vec == 4) rc = big ? run_vec<4, 32>(ctx, warps, iters, d_out, &ms) : run_vec<4, 16>(ctx, warps, iters, d_out, &ms);
+  else qmb_set_error("vec must be 1, 2 or 4");
+  cudaFree(d_out);
+  if (rc != QMB_OK) return rc;
+  *gather_adds_per_s = (double)ctx->sm_count * warps * 32.0 * (big ? 32.0 : 16.0) * (double)iters / ((double)ms * 1e-3);
+  return QMB_OK;
+}
+
+// The ceiling k_scan is judged against: LDS.32 + FADD streams on 12 warps per SM (its consumer
+// warp count), 32 independent gathers per lane per iteration.
+extern "C" int qmb_microbench_smem_pipe(qmb_ctx_t ctx, int32_t iters, double *gather_adds_per_s) {
+  return qmb_microbench_smem_pipe_ex(ctx, iters, 1, 12, gather_adds_per_s);
+}

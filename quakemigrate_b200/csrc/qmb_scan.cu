@@ -234,7 +234,10 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
         // least NPW*K/2 independent LDS are outstanding whatever order ptxas picks.
         constexpr int H = NPW / 2;
         auto load_off = [&](int sl, uint32_t (&off)[NPW]) {
-          if constexpr (NPW == 4) {
+          if constexpr (MODE == 3) {  // ablation: no offset fetch (timing only, results meaningless)
+#pragma unroll
+            for (int q = 0; q < NPW; ++q) off[q] = 4u * q + (uint32_t)(sl & 3);
+          } else if constexpr (NPW == 4) {
             uint32_t a, b;
             asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(tau_addr + (uint32_t)sl * NB * 2u));
             off[0] = a & 0xffffu; off[1] = a >> 16; off[2] = b & 0xffffu; off[3] = b >> 16;
@@ -307,6 +310,16 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
             for (int o = 16; o > 0; o >>= 1) nodesum += __shfl_xor_sync(0xffffffffu, nodesum, o);
             if (lane == 0) atomicAdd(&p.coa_map[local], nodesum);
           }
+        }
+        continue;
+      }
+      if constexpr (MODE == 2) {  // ablation: no epilogue (timing only): keep the stacks alive cheaply
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          float t = acc[0][k];
+#pragma unroll
+          for (int q = 1; q < NPW; ++q) t += acc[q][k];
+          m1[k] = fmaxf(m1[k], t);
         }
         continue;
       }
@@ -571,7 +584,13 @@ int dispatch_scan(qmb_ctx *ctx, const QmbVariant &v, const ScanParams &p, int gr
     case 4: return launch_scan<12, 4, 8, MODE, 16>(ctx, p, grid, smem);
     case 5: return launch_scan<12, 8, 4, MODE, 16>(ctx, p, grid, smem);
     case 6: return launch_scan<8, 4, 8, MODE, 16>(ctx, p, grid, smem);
-    case 7: return launch_scan<12, 4, 8, MODE, 32>(ctx, p, grid, smem);
+    case 7:
+      if constexpr (MODE == 0) {  // QMB_ABLATE=2|3: timing-only ablations of the default kernel
+        const char *ab = getenv("QMB_ABLATE");
+        if (ab && atoi(ab) == 2) return launch_scan<12, 4, 8, 2, 32>(ctx, p, grid, smem);
+        if (ab && atoi(ab) == 3) return launch_scan<12, 4, 8, 3, 32>(ctx, p, grid, smem);
+      }
+      return launch_scan<12, 4, 8, MODE, 32>(ctx, p, grid, smem);
     case 8: return launch_scan<15, 4, 8, MODE, 32>(ctx, p, grid, smem);
     case 9: return launch_scan<15, 4, 8, MODE, 16>(ctx, p, grid, smem);
   }
