@@ -55,6 +55,9 @@ def parse_args():
     ap.add_argument("--variant", type=int, default=-1, help="kernel tiling variant id; -1 = library default")
     ap.add_argument("--samples", type=int, default=0, help="override n_samples (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: shard the FIXED workload grid over the ranks (default: weak, one "
+                         "workload-sized slab per GPU)")
     return ap.parse_args()
 
 
@@ -205,11 +208,15 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
     from quakemigrate_b200.core import Engine
 
     base = syn.CONFIGS[args.workload]
-    cfg = global_config(base, world, args.samples)
-    nx_per = base.grid[0]
-    x0, x1 = rank * nx_per, (rank + 1) * nx_per
+    if args.strong:
+        from quakemigrate_b200.sharding import slab_bounds
+        cfg = base.scaled(n_samples=args.samples or base.n_samples, name=base.name)
+        x0, x1 = slab_bounds(cfg.grid[0], world, rank)
+    else:
+        cfg = global_config(base, world, args.samples)
+        x0, x1 = rank * base.grid[0], (rank + 1) * base.grid[0]
     prob = syn.make_problem(cfg, with_waveforms=True, x_range=(x0, x1))
-    N_local = nx_per * cfg.grid[1] * cfg.grid[2]
+    N_local = (x1 - x0) * cfg.grid[1] * cfg.grid[2]
     N_global, T, S = cfg.n_nodes, cfg.n_samples, cfg.n_rows
     P = prob.n_total
 
@@ -293,11 +300,12 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong" if args.strong else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {
             "workload": f"{cfg.name}: {cfg.grid[0]}x{cfg.grid[1]}x{cfg.grid[2]} grid "
-                        f"({base.grid[0]}x{base.grid[1]}x{base.grid[2]} x-slab per GPU), {S} onset rows, "
+                        f"({x1 - x0}x{cfg.grid[1]}x{cfg.grid[2]} x-slab on rank {rank}), {S} onset rows, "
                         f"{T} samples @ {cfg.sampling_rate} Hz, {cfg.position} STA/LTA, detect() scan",
             "n_nodes": N_global, "n_rows": S, "n_samples": T, "fsmp": prob.fsmp, "lsmp": prob.lsmp,
             "parallelism": f"node-slab x{world}", "cache": "L2 flushed (256 MiB memset) before every timed step",
