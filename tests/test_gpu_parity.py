@@ -245,3 +245,20 @@ def test_fine_grid_with_many_shared_offsets(engine):
     want = O.detect_fused(onsets, prob.traveltimes, prob.fsmp, prob.lsmp, cfg.n_rows, threads=4)
     _check_detect(got, want)
     lut.free()
+
+
+def test_onset_clip_floor_and_log(engine):
+    """np.clip(onsets, 0.01, inf) before the log (lib.py:93-94): zeros, negatives and tiny values."""
+    grid, S, T, fsmp, lsmp = (5, 5, 4), 4, 90, 2, 20
+    onsets, tau = syn.random_problem(8, grid, S, T, fsmp, lsmp)
+    rng = np.random.default_rng(8)
+    sel = rng.random(onsets.shape)
+    onsets[sel < 0.10] = 0.0
+    onsets[(sel >= 0.10) & (sel < 0.15)] = -3.0
+    onsets[(sel >= 0.15) & (sel < 0.20)] = 1e-7
+    onsets[(sel >= 0.20) & (sel < 0.25)] = 0.01
+    lut = engine.upload_lut(tau)
+    got = engine.detect(lut, onsets, fsmp, lsmp, S)
+    want = O.find_max_coa(O.migrate(onsets, tau, fsmp, lsmp, S, threads=2), threads=2)
+    _check_detect(got, want)
+    lut.free()
