@@ -262,3 +262,25 @@ def test_onset_clip_floor_and_log(engine):
     want = O.find_max_coa(O.migrate(onsets, tau, fsmp, lsmp, S, threads=2), threads=2)
     _check_detect(got, want)
     lut.free()
+
+
+@pytest.mark.parametrize("n_levels,jitter", [(3, 1e-9), (2, 3e-8), (6, 1e-12)])
+def test_near_ties_below_fp32_resolution(engine, n_levels, jitter):
+    """
+    Onsets drawn from a few discrete levels times (1 + k*jitter): many nodes have stacks that
+    differ only far below float32 resolution (but not exactly), so the fp32 pass cannot rank them
+    and the float64 pair / slow paths must reproduce the reference's arg-max exactly.
+    """
+    grid, S, T, fsmp, lsmp = (7, 6, 6), 5, 180, 4, 24
+    rng = np.random.default_rng(n_levels * 1000 + int(-np.log10(jitter)))
+    levels = np.array([0.5, 0.8, 1.3, 2.0, 3.1, 4.7])[:n_levels]
+    total = fsmp + T + lsmp
+    onsets = levels[rng.integers(0, n_levels, size=(S, total))] * (1.0 + jitter * rng.integers(0, 4, size=(S, total)))
+    tau = rng.integers(0, lsmp + 1, size=grid + (S,), dtype=np.int32)
+    lut = engine.upload_lut(tau)
+    info_ms = engine.detect_device(lut, engine.upload_onsets(onsets), fsmp, lsmp, S)
+    got = engine.detect_fetch(T)
+    want = O.find_max_coa(O.migrate(onsets, tau, fsmp, lsmp, S, threads=2), threads=2)
+    assert info_ms["slow_samples"] > 0          # the case really exercises the slow path
+    _check_detect(got, want)
+    lut.free()
