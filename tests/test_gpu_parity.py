@@ -284,3 +284,24 @@ def test_near_ties_below_fp32_resolution(engine, n_levels, jitter):
     assert info_ms["slow_samples"] > 0          # the case really exercises the slow path
     _check_detect(got, want)
     lut.free()
+
+
+def test_span_too_wide_is_an_error_not_a_fallback(engine):
+    """Travel-time range inside one tile beyond what shared memory can stage -> QMB_ERR_UNSUPPORTED."""
+    from quakemigrate_b200.core import QmbError
+    grid, S = (4, 4, 4), 3
+    tau = np.zeros(grid + (S,), dtype=np.int32)
+    tau[0, 0, 0, :] = 20000                       # one node 20000 samples away from its neighbours
+    with pytest.raises(QmbError, match="too wide|too large"):
+        engine.upload_lut(tau)
+
+
+def test_long_trace_small_grid(engine):
+    """Hundreds of thousands of samples: index arithmetic, many time tiles, few node tiles."""
+    grid, S, T, fsmp, lsmp = (3, 3, 3), 3, 300_001, 7, 40
+    onsets, tau = syn.random_problem(12, grid, S, T, fsmp, lsmp)
+    lut = engine.upload_lut(tau)
+    got = engine.detect(lut, onsets, fsmp, lsmp, S)
+    want = O.detect_fused(onsets, tau, fsmp, lsmp, S, threads=O.default_threads())
+    _check_detect(got, want)
+    lut.free()
