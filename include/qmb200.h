@@ -174,6 +174,34 @@ int qmb_detect(qmb_ctx_t ctx, qmb_lut_t lut, const double *onsets, int32_t n_row
                int64_t n_total, int32_t fsmp, int32_t lsmp, int32_t available, double *max_coa,
                double *max_norm_coa, int64_t *max_coa_idx);
 
+/* --- detect output stage ----------------------------------------------------
+ * qmb_detect_fetch_quantised: the last detect result in the integer form ScanmSEED.append stores
+ * (quakemigrate/io/scanmseed.py:102-130, _data2int :226-240), produced on the device:
+ *   coa_q, coa_n_q  int32 (n): round(min(x, 21474) * 1e5), numpy rounding (half to even)
+ *   ijk             int32 (n, 3): C-order unravel of max_coa_idx by node_count (lut.py:165-166)
+ *   xyz             float64 (n, 3): ll_corner + ijk * node_spacing (lut.py:177), grid projection
+ *   z_q             int32 (n): round(xyz[:, 2] * z_factor), z_factor = 1e3 * ucf (scanmseed.py:127)
+ * Any output pointer may be null.  Longitude/latitude need the inverse map projection
+ * (lut.py:236, pyproj): host work on `xyz`, outside this library. */
+int qmb_detect_fetch_quantised(qmb_ctx_t ctx, const int32_t *node_count /* 3 */,
+                               const double *ll_corner /* 3 */, const double *node_spacing /* 3 */,
+                               double z_factor, int32_t *coa_q, int32_t *coa_n_q, int32_t *ijk,
+                               double *xyz, int32_t *z_q, int32_t n_samples);
+
+/* STEIM-1 / STEIM-2 data sections of miniSEED records (HOST code, no GPU involved): what
+ * st.write(format="MSEED", encoding="STEIM2") produces through obspy/libmseed in the reference
+ * (scanmseed.py:216-224; STEIM-1 is its fall-back when a difference exceeds 30 bits).
+ * qmb_steim_encode packs as many of samples[0..n) as fit into n_frames 64-byte frames (`out`,
+ * n_frames*64 bytes, zero-filled here), d0 = first difference (samples[0] minus the last sample of
+ * the previous record, 0 for the first record of a trace); *n_packed = samples consumed.
+ * Returns QMB_ERR_UNSUPPORTED when a difference does not fit the encoding.
+ * qmb_steim_decode is the inverse for one record (first_diff nullable) and verifies the reverse
+ * integration constant. */
+int qmb_steim_encode(const int32_t *samples, int64_t n, int32_t d0, int32_t version, int32_t n_frames,
+                     uint8_t *out, int64_t *n_packed);
+int qmb_steim_decode(const uint8_t *frames, int32_t n_frames, int32_t version, int64_t n_samples,
+                     int32_t *out, int32_t *first_diff);
+
 /* --- locate: detect outputs + the marginal window of the 4-D map ------------------------------
  * After a detect pass over the whole span, re-migrates only samples [win0, win1) (end-exclusive,
  * quakemigrate/io/event.py:433-435) and returns

@@ -99,6 +99,12 @@ SIGNATURES = {
     "qmb_detect_fetch": (ctypes.c_int, [c_void_p, c_dPt, c_dPt, c_i64Pt, c_int32]),
     "qmb_detect": (ctypes.c_int, [c_void_p, c_void_p, c_dPt, c_int32, c_int64, c_int32, c_int32, c_int32,
                                   c_dPt, c_dPt, c_i64Pt]),
+    "qmb_detect_fetch_quantised": (ctypes.c_int, [c_void_p, c_i32Pt, c_dPt, c_dPt, c_double, c_void_p,
+                                                  c_void_p, c_void_p, c_void_p, c_void_p, c_int32]),
+    "qmb_steim_encode": (ctypes.c_int, [c_i32Pt, c_int64, c_int32, c_int32, c_int32, c_void_p,
+                                        ctypes.POINTER(c_int64)]),
+    "qmb_steim_decode": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_int64, c_i32Pt,
+                                        ctypes.POINTER(c_int32)]),
     "qmb_locate_window": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                          c_int32, c_int32, c_void_p, c_void_p]),
     "qmb_gaufilt3d": (ctypes.c_int, [c_void_p, c_dPt, c_int32, c_int32, c_int32, c_double, c_dPt]),

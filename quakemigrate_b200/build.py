@@ -19,7 +19,8 @@ import sys
 HERE = pathlib.Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libqmb200.so"
-SOURCES = ["qmb_api.cu", "qmb_lut.cu", "qmb_onset.cu", "qmb_scan.cu", "qmb_legacy.cu", "qmb_locate.cu"]
+SOURCES = ["qmb_api.cu", "qmb_lut.cu", "qmb_onset.cu", "qmb_scan.cu", "qmb_legacy.cu", "qmb_locate.cu",
+           "qmb_output.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

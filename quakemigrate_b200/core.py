@@ -348,6 +348,27 @@ class Engine:
         _lib.check(self._lib.qmb_detect_fetch(self._h, max_coa, max_norm, idx, int(n_samples)))
         return max_coa, max_norm, idx
 
+    def detect_fetch_quantised(self, n_samples: int, node_count, ll_corner, node_spacing,
+                               z_factor: float, want=("coa", "coa_n", "ijk", "xyz", "z")):
+        """
+        The last detect result in the integer form ``ScanmSEED.append`` stores
+        (io/scanmseed.py:102-130), quantised on the device: dict with ``coa``, ``coa_n`` (int32,
+        clip 21474, x1e5, half-to-even), ``ijk`` (int32 (n, 3), C-order unravel, lut.py:165-166),
+        ``xyz`` (float64 (n, 3) grid coordinates, lut.py:177) and ``z`` (int32, ``xyz[:, 2]`` x
+        ``z_factor`` = 1e3 * ucf).
+        """
+        n = int(n_samples)
+        bufs = {"coa": np.empty(n, np.int32), "coa_n": np.empty(n, np.int32),
+                "ijk": np.empty((n, 3), np.int32), "xyz": np.empty((n, 3), np.double),
+                "z": np.empty(n, np.int32)}
+        ptr = {k: (v.ctypes.data_as(ctypes.c_void_p) if k in want else None) for k, v in bufs.items()}
+        _lib.check(self._lib.qmb_detect_fetch_quantised(
+            self._h, np.ascontiguousarray(node_count, dtype=np.int32),
+            np.ascontiguousarray(ll_corner, dtype=np.double),
+            np.ascontiguousarray(node_spacing, dtype=np.double), float(z_factor),
+            ptr["coa"], ptr["coa_n"], ptr["ijk"], ptr["xyz"], ptr["z"], n))
+        return {k: v for k, v in bufs.items() if k in want}
+
     def detect(self, lut: DeviceLUT, onsets, fsmp: int, lsmp: int, available: int):
         """
         ``find_max_coa(migrate(onsets, lut, fsmp, lsmp, available))`` fused on the device

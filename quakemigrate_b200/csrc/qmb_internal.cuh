@@ -116,6 +116,8 @@ struct qmb_ctx {
   DevBuf<unsigned long long> slow_idx;
   DevBuf<unsigned char> flush;  // L2 eviction scratch (benchmarks)
   DevBuf<double> stage_lin;     // H2D staging of linear onsets (reused across calls)
+  DevBuf<int32_t> q_i32;        // output stage: quantised channels + unravelled indices
+  DevBuf<double> q_f64;         // output stage: grid coordinates
   struct qmb_onsets *tmp_onsets = nullptr;  // onset rows of the one-call qmb_detect (reused)
   int32_t last_n_samples = 0;
   // pinned staging for small D2H

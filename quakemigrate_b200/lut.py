@@ -130,13 +130,95 @@ class LUT(Grid3D):
 
 
 # ------------------------------------------------------------------------------------------------
+# the one map projection the reference's examples use, so that ``index2coord`` can finish its job
+# (lut.py:236: pyproj transform grid -> lon/lat) without pyproj
+# ------------------------------------------------------------------------------------------------
+class LambertConformalConic:
+    """
+    Ellipsoidal Lambert conformal conic with two standard parallels (``+proj=lcc``; Snyder,
+    "Map projections -- a working manual", USGS PP 1395, eqs. 15-1..15-11, 14-15, 7-9) -- the
+    published algorithm PROJ implements.  ``forward`` / ``inverse`` act on (n, 3) arrays
+    ``[lon, lat, z]`` <-> ``[x, y, z]`` (z passes through), i.e. they play ``coord2grid`` /
+    ``grid2coord`` (lut.py:182-243) for a ``longlat`` coordinate projection on the same datum.
+    Pinned by the X / Y channels of the reference's golden .scanmseed (tests/test_scanmseed.py).
+    """
+
+    ELLIPSOIDS = {"WGS84": (6378137.0, 1.0 / 298.257223563), "GRS80": (6378137.0, 1.0 / 298.257222101)}
+    UNITS = {"m": 1.0, "km": 1000.0}
+
+    def __init__(self, lon_0, lat_0, lat_1, lat_2=None, ellps="WGS84", units="m", x_0=0.0, y_0=0.0):
+        self.a, f = self.ELLIPSOIDS[ellps]
+        self.e = np.sqrt(2.0 * f - f * f)
+        self.unit = self.UNITS[units]
+        self.unit_conversion_factor = self.unit  # pyproj axis_info[0].unit_conversion_factor
+        self.lon_0, self.x_0, self.y_0 = np.radians(lon_0), x_0, y_0
+        phi0, phi1 = np.radians(lat_0), np.radians(lat_1)
+        phi2 = phi1 if lat_2 is None else np.radians(lat_2)
+        if abs(phi1 - phi2) < 1e-12:
+            self.n = np.sin(phi1)
+        else:
+            self.n = (np.log(self._m(phi1)) - np.log(self._m(phi2))) / (
+                np.log(self._t(phi1)) - np.log(self._t(phi2)))
+        self.F = self._m(phi1) / (self.n * self._t(phi1) ** self.n)
+        self.rho0 = self.a * self.F * self._t(phi0) ** self.n
+
+    def _m(self, phi):
+        return np.cos(phi) / np.sqrt(1.0 - (self.e * np.sin(phi)) ** 2)
+
+    def _t(self, phi):
+        es = self.e * np.sin(phi)
+        return np.tan(np.pi / 4 - phi / 2) / ((1.0 - es) / (1.0 + es)) ** (self.e / 2)
+
+    def forward(self, coord):
+        coord = np.atleast_2d(np.asarray(coord, dtype=float))
+        lam, phi = np.radians(coord[:, 0]), np.radians(coord[:, 1])
+        rho = self.a * self.F * self._t(phi) ** self.n
+        theta = self.n * (lam - self.lon_0)
+        out = coord.copy()
+        out[:, 0] = (rho * np.sin(theta) + self.x_0) / self.unit
+        out[:, 1] = (self.rho0 - rho * np.cos(theta) + self.y_0) / self.unit
+        return out
+
+    def inverse(self, grid):
+        grid = np.atleast_2d(np.asarray(grid, dtype=float))
+        x = grid[:, 0] * self.unit - self.x_0
+        y = self.rho0 - (grid[:, 1] * self.unit - self.y_0)
+        sgn = np.sign(self.n)
+        rho = sgn * np.hypot(x, y)
+        theta = np.arctan2(sgn * x, sgn * y)
+        t = (rho / (self.a * self.F)) ** (1.0 / self.n)
+        phi = np.pi / 2 - 2 * np.arctan(t)
+        for _ in range(12):  # Snyder 7-9; converges to 1e-15 in ~5 rounds
+            es = self.e * np.sin(phi)
+            phi = np.pi / 2 - 2 * np.arctan(t * ((1.0 - es) / (1.0 + es)) ** (self.e / 2))
+        out = grid.copy()
+        out[:, 0] = np.degrees(theta / self.n + self.lon_0)
+        out[:, 1] = np.degrees(phi)
+        return out
+
+    @classmethod
+    def from_proj_string(cls, srs: str):
+        """Parse a PROJ string (``+proj=lcc +units=km +lon_0=...``); None if it is not this projection."""
+        kv = dict(tok[1:].split("=", 1) if "=" in tok else (tok[1:], "")
+                  for tok in srs.split() if tok.startswith("+"))
+        if kv.get("proj") != "lcc":
+            return None
+        ellps = kv.get("ellps", kv.get("datum", "WGS84"))
+        if ellps not in cls.ELLIPSOIDS or kv.get("units", "m") not in cls.UNITS:
+            return None
+        return cls(float(kv.get("lon_0", 0.0)), float(kv.get("lat_0", 0.0)), float(kv["lat_1"]),
+                   float(kv["lat_2"]) if "lat_2" in kv else None, ellps, kv.get("units", "m"),
+                   float(kv.get("x_0", 0.0)), float(kv.get("y_0", 0.0)))
+
+
+# ------------------------------------------------------------------------------------------------
 # reading the reference's pickled LUTs without pyproj
 # ------------------------------------------------------------------------------------------------
 class _Opaque:
     """Stand-in for classes we cannot (and need not) import, e.g. pyproj.Proj."""
 
     def __init__(self, *a, **k):
-        pass
+        self.args, self.kwargs = a, k
 
     def __setstate__(self, state):
         self.__dict__["state"] = state
@@ -170,6 +252,17 @@ def read_reference_lut(path, grid2coord=None) -> LUT:
         raise ValueError(f"unrecognised LUT pickle (keys: {sorted(d)[:20]})")
     lut = LUT(tt, node_count, spacing if spacing is not None else np.ones(3),
               ll if ll is not None else np.zeros(3), phases=d.get("phases"), grid2coord=grid2coord)
+    # grid projection: rebuilt from the PROJ string pyproj pickles (Proj.__reduce__ -> (srs,)) when it
+    # is the Lambert conformal conic of the reference's examples; otherwise left to the caller
+    gproj, cproj = d.get("grid_proj"), d.get("coord_proj")
+    gargs, cargs = getattr(gproj, "args", ()), getattr(cproj, "args", ())
+    if gargs and isinstance(gargs[0], str):
+        lut.grid_proj_string = gargs[0]
+        proj = LambertConformalConic.from_proj_string(gargs[0])
+        if proj is not None:
+            lut.unit_conversion_factor = proj.unit_conversion_factor
+            if grid2coord is None and cargs and "+proj=longlat" in str(cargs[0]):
+                lut.grid2coord, lut.coord2grid_fn = proj.inverse, proj.forward
     sd = d.get("station_data")
     if sd is not None and hasattr(sd, "__getitem__"):
         try:
