@@ -32,7 +32,7 @@ import logging
 import numpy as np
 
 from .core import DeviceOnsets, Engine
-from .onsets import Onset
+from .onsets import DataAvailabilityException, Onset
 from .synthetic import time2sample
 
 
@@ -208,6 +208,55 @@ class QuakeScan:
             logging.debug("detect chunk %d", i)
             time, max_coa, max_coa_n, coord, _ = self._compute(data)
             yield time, max_coa, max_coa_n, coord
+
+    def continuous_compute(self, starttime, chunks, run, continuous_write=False, device_output=True):
+        """
+        ``_continuous_compute`` (scan.py:406-467) over already-read waveform chunks, INCLUDING its
+        output stage: every timestep is appended to a :class:`~quakemigrate_b200.scanmseed.ScanmSEED`
+        (scanmseed.py:74-150) and day files are written under ``<run>/detect/scanmseed``.
+
+        ``chunks[i]`` is the waveform container of timestep ``i`` (read with the pads of
+        ``onset.pad(timestep)``) or ``None`` when the archive had nothing usable -- the reference
+        stores such a step as zeros (``ScanmSEED.empty``, scan.py:454-461).  With
+        ``device_output`` the COA / COA_N / Z channels are quantised on the device and only int32
+        channels plus grid coordinates come back (``qmb_detect_fetch_quantised``); otherwise the
+        float64 traces are fetched and quantised on the host like the reference.  Both give
+        byte-identical files.  Returns ``(ScanmSEED, [availability dict or None per step])``.
+        """
+        from .scanmseed import ScanmSEED
+
+        coalescence = ScanmSEED(run, continuous_write, self.scan_rate)
+        self.pre_pad, self.post_pad = self.onset.pad(self.timestep)
+        ucf = getattr(self.lut, "unit_conversion_factor", 1.0)
+        availability = []
+        for i, data in enumerate(chunks):
+            if data is None:
+                coalescence.empty(starttime, self.timestep, i, f"no data for timestep {i}", ucf)
+                availability.append(None)
+                continue
+            try:
+                if device_output:
+                    onsets, onset_data, dlut, dev, owned, fsmp, lsmp, avail = self._prepare(data)
+                    try:
+                        n_samples = dev.n_total - fsmp - lsmp
+                        if n_samples <= 0:
+                            raise ValueError("Data array smaller than coalescence array.")
+                        self.engine.detect_device(dlut, dev, fsmp, lsmp, avail)
+                        coalescence.append_from_engine(data.starttime + self.pre_pad, self.engine,
+                                                       n_samples, self.lut, ucf)
+                    finally:
+                        if owned:
+                            dev.free()
+                else:
+                    time, max_coa, max_coa_n, coord, onset_data = self._compute(data)
+                    coalescence.append(time, max_coa, max_coa_n, coord, ucf)
+                availability.append(dict(onset_data.availability))
+            except DataAvailabilityException as e:
+                coalescence.empty(starttime, self.timestep, i, str(e), ucf)
+                availability.append(None)
+        if not coalescence.written:
+            coalescence.write()
+        return coalescence, availability
 
     def close(self):
         for dlut in self._lut_cache.values():

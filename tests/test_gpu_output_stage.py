@@ -98,3 +98,44 @@ def test_files_from_device_and_host_paths_are_identical(tmp_path):
                                     g.unit_conversion_factor)
     assert stats["npts"] == cfg.n_samples
     np.testing.assert_allclose(data["COA"].values, max_coa, atol=0.5e-5 * 1.0000001)
+
+
+def test_continuous_compute_writes_the_same_file_either_way(tmp_path):
+    """QuakeScan.continuous_compute (scan.py:406-467): three timesteps, the middle one without data."""
+    from test_gpu_scan_api import _problem
+
+    from quakemigrate_b200.core import Engine
+    from quakemigrate_b200.onsets import STALTAOnset, WaveformData
+    from quakemigrate_b200.scan import QuakeScan
+
+    cfg, prob, lut, data = _problem()
+    meta = json.loads((GOLD / "golden_iceland_grid.json").read_text())
+    proj = LambertConformalConic.from_proj_string(meta["grid_proj"])
+    lut.grid2coord, lut.unit_conversion_factor = proj.inverse, proj.unit_conversion_factor
+    sr = cfg.sampling_rate
+    with Engine(0) as eng:
+        onset = STALTAOnset(engine=eng, sampling_rate=sr, position="classic")
+        scan = QuakeScan(lut, onset, engine=eng, timestep=4.0)
+        pre, post = scan.set_pads(scan.timestep)
+        n_chunk = int(round((pre + post + scan.timestep) * sr))
+        t_first = 1_404_067_325.0  # 2014-06-29 18:42:05 UTC
+        chunks = []
+        for i in range(3):
+            if i == 1:
+                chunks.append(None)
+                continue
+            o = i * int(scan.timestep * sr)
+            ch = {st: {c: v[o:o + n_chunk] for c, v in comps.items()} for st, comps in data.channels.items()}
+            chunks.append(WaveformData(ch, starttime=t_first + i * scan.timestep - pre, sampling_rate=sr))
+        files = []
+        for mode in (True, False):
+            run = tmp_path / ("dev" if mode else "host")
+            coalescence, availability = scan.continuous_compute(t_first, chunks, run, device_output=mode)
+            assert coalescence.written and availability[1] is None and sum(availability[0].values()) > 0
+            files.append(run / "detect" / "scanmseed" / "2014_180.scanmseed")
+        scan.close()
+    assert files[0].read_bytes() == files[1].read_bytes()
+    df, stats = sm.read_scanmseed(tmp_path / "dev", t_first, t_first + 12.0, 0.0, lut.unit_conversion_factor)
+    n = int(scan.timestep * sr)
+    assert stats["npts"] == 3 * n
+    assert (df["COA"].values[n:2 * n] == 0).all() and (df["COA"].values[:n] > 0).all()
