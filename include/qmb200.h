@@ -71,7 +71,14 @@ enum {
 };
 
 enum { QMB_STALTA_CLASSIC = 0, QMB_STALTA_CENTRED = 1, QMB_STALTA_RECURSIVE = 2 };
-enum { QMB_TRANSFORM_NONE = 0, QMB_TRANSFORM_ENERGY = 1, QMB_TRANSFORM_ABS = 2 };
+/* signal_transform of STALTAOnset._onset (stalta.py:516-523): x^2, |x|, |hilbert(x)|, |hilbert(x)|^2 */
+enum {
+  QMB_TRANSFORM_NONE = 0,
+  QMB_TRANSFORM_ENERGY = 1,
+  QMB_TRANSFORM_ABS = 2,
+  QMB_TRANSFORM_ENV = 3,
+  QMB_TRANSFORM_ENV_SQUARED = 4
+};
 
 typedef struct qmb_ctx *qmb_ctx_t;       /* one per (process, GPU) */
 typedef struct qmb_lut *qmb_lut_t;       /* device-resident travel-time table (node slab) */
@@ -152,6 +159,45 @@ int qmb_onsets_from_waveforms(qmb_ctx_t ctx, const double *waveforms, int32_t n_
                               double *onsets_out /* nullable, (n_rows, n_total) */,
                               qmb_onsets_t *out);
 int qmb_onsets_free(qmb_onsets_t onsets);
+
+/* --- waveform pre-processing ---------------------------------------------------
+ * pre_process (quakemigrate/signal/onsets/stalta.py:203-209) and util.decimate
+ * (quakemigrate/util.py:499-518) for blocks of equally long float64 traces kept on the device:
+ *   detrend("linear") + detrend("constant")  (detrend != 0)
+ *   -> cosine taper over int(taper_fraction * n) samples at either end  (obspy Trace.taper)
+ *   -> IIR filter given as scipy second-order sections, (n_sections, 6) rows b0 b1 b2 a0 a1 a2,
+ *      n_sections in 0..4 (0: no filter); zerophase != 0: forward, then over the reversed trace
+ *      (obspy.signal.filter.bandpass/lowpass(zerophase=True))
+ *   -> keep every `decimate`-th sample (Trace.decimate(factor, no_filter=True)).
+ * qmb_waveforms_filter reads channels `channels[0..n_sel)` of `in` (null: all) and writes channels
+ * [out_chan0, out_chan0 + n_sel) of `out`, whose traces must hold ceil(n / decimate) samples.
+ * kernel_ms (nullable): device time of the kernels of this call (CUDA events).
+ * qmb_onsets_from_device_waveforms is qmb_onsets_from_waveforms on such a block: raw traces ->
+ * filtered traces -> onset functions without a host round trip.
+ * qmb_preprocess is the one-call form with host buffers. */
+typedef struct qmb_waveforms *qmb_waveforms_t;
+int qmb_waveforms_alloc(qmb_ctx_t ctx, int32_t n_channels, int64_t n, qmb_waveforms_t *out);
+int qmb_waveforms_upload(qmb_ctx_t ctx, const double *x, int32_t n_channels, int64_t n,
+                         qmb_waveforms_t *out);
+int qmb_waveforms_fetch(qmb_waveforms_t w, int32_t chan0, int32_t n_chan, double *host);
+int qmb_waveforms_free(qmb_waveforms_t w);
+int qmb_waveforms_filter(qmb_ctx_t ctx, qmb_waveforms_t in, const int32_t *channels, int32_t n_sel,
+                         const double *sos, int32_t n_sections, int32_t detrend, double taper_fraction,
+                         int32_t zerophase, int32_t decimate, qmb_waveforms_t out, int32_t out_chan0,
+                         float *kernel_ms);
+int qmb_onsets_from_device_waveforms(qmb_ctx_t ctx, qmb_waveforms_t w, int32_t n_rows,
+                                     const int32_t *row_ptr, const int32_t *row_chan,
+                                     const int32_t *nsta, const int32_t *nlta, int32_t position,
+                                     int32_t transform, double min_onset_value,
+                                     double *onsets_out /* nullable */, qmb_onsets_t *out);
+int qmb_preprocess(qmb_ctx_t ctx, const double *x, int32_t n_channels, int64_t n, const double *sos,
+                   int32_t n_sections, int32_t detrend, double taper_fraction, int32_t zerophase,
+                   int32_t decimate, double *out /* (n_channels, ceil(n / decimate)) */);
+
+/* np.abs(scipy.signal.hilbert(x, axis=-1)) of a host (n_channels, n) block: the envelope behind the
+ * "env" / "env_squared" transforms (stalta.py:520-523).  The FFTs are cuFFT's (dlopen'ed on first
+ * use); weighting and modulus are this library's kernels. */
+int qmb_envelope(qmb_ctx_t ctx, const double *x, int32_t n_channels, int64_t n, double *out);
 
 /* batched STA/LTA on (n_channels, n) host arrays; `onset` must arrive pre-filled like the
  * reference wrappers do (lib.py:204,242,281) -- only the valid range is written. */

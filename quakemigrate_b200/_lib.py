@@ -37,7 +37,7 @@ QMB_NCCL_ID_BYTES = 128
 STATUS_NAMES = {0: "QMB_OK", 1: "QMB_ERR_CUDA", 2: "QMB_ERR_ARG", 3: "QMB_ERR_UNSUPPORTED",
                 4: "QMB_ERR_NCCL", 5: "QMB_ERR_STATE"}
 STALTA_POSITION = {"classic": 0, "centred": 1, "recursive": 2}
-TRANSFORM = {"none": 0, "energy": 1, "abs": 2}
+TRANSFORM = {"none": 0, "energy": 1, "abs": 2, "env": 3, "env_squared": 4}
 
 
 class LutInfo(ctypes.Structure):
@@ -93,6 +93,19 @@ SIGNATURES = {
                                                  c_i32Pt, c_i32Pt, c_i32Pt, c_int32, c_int32, c_double,
                                                  c_void_p, ctypes.POINTER(c_void_p)]),
     "qmb_onsets_free": (ctypes.c_int, [c_void_p]),
+    "qmb_waveforms_alloc": (ctypes.c_int, [c_void_p, c_int32, c_int64, ctypes.POINTER(c_void_p)]),
+    "qmb_waveforms_upload": (ctypes.c_int, [c_void_p, c_dPt, c_int32, c_int64, ctypes.POINTER(c_void_p)]),
+    "qmb_waveforms_fetch": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_dPt]),
+    "qmb_waveforms_free": (ctypes.c_int, [c_void_p]),
+    "qmb_waveforms_filter": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int32,
+                                            c_int32, c_double, c_int32, c_int32, c_void_p, c_int32,
+                                            c_void_p]),
+    "qmb_onsets_from_device_waveforms": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_i32Pt, c_i32Pt,
+                                                        c_i32Pt, c_i32Pt, c_int32, c_int32, c_double,
+                                                        c_void_p, ctypes.POINTER(c_void_p)]),
+    "qmb_preprocess": (ctypes.c_int, [c_void_p, c_dPt, c_int32, c_int64, c_void_p, c_int32, c_int32,
+                                      c_double, c_int32, c_int32, c_dPt]),
+    "qmb_envelope": (ctypes.c_int, [c_void_p, c_dPt, c_int32, c_int64, c_dPt]),
     "qmb_sta_lta": (ctypes.c_int, [c_void_p, c_dPt, c_int32, c_int64, c_int32, c_int32, c_int32, c_dPt]),
     "qmb_detect_device": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                          c_void_p]),

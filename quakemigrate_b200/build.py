@@ -20,7 +20,7 @@ HERE = pathlib.Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libqmb200.so"
 SOURCES = ["qmb_api.cu", "qmb_lut.cu", "qmb_onset.cu", "qmb_scan.cu", "qmb_legacy.cu", "qmb_locate.cu",
-           "qmb_output.cu"]
+           "qmb_output.cu", "qmb_preprocess.cu", "qmb_envelope.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

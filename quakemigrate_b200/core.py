@@ -24,7 +24,8 @@ from . import _lib
 from ._lib import QmbError, c_int32, c_int64, stalta_header_t  # noqa: F401
 
 __all__ = ["migrate", "find_max_coa", "overlapping_sta_lta", "centred_sta_lta",
-           "recursive_sta_lta", "Engine", "DeviceLUT", "DeviceOnsets", "DeviceGrids", "QmbError"]
+           "recursive_sta_lta", "Engine", "DeviceLUT", "DeviceOnsets", "DeviceGrids", "DeviceWaveforms",
+           "QmbError"]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -180,6 +181,35 @@ class DeviceOnsets:
             pass
 
 
+class DeviceWaveforms:
+    """Handle to a block of float64 traces ``(n_channels, n)`` resident on the device."""
+
+    def __init__(self, engine, handle, n_channels, n):
+        self.engine, self._h = engine, handle
+        self.n_channels, self.n = int(n_channels), int(n)
+
+    @property
+    def shape(self):
+        return (self.n_channels, self.n)
+
+    def fetch(self, chan0: int = 0, n_chan: int | None = None) -> np.ndarray:
+        n_chan = self.n_channels - chan0 if n_chan is None else n_chan
+        out = np.empty((n_chan, self.n), dtype=np.double)
+        _lib.check(_lib.load().qmb_waveforms_fetch(self._h, int(chan0), int(n_chan), out))
+        return out
+
+    def free(self):
+        if self._h:
+            _lib.load().qmb_waveforms_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class Engine:
     """One GPU context: streams, scratch, optional NCCL communicator."""
 
@@ -322,6 +352,85 @@ class Engine:
             out.ctypes.data_as(ctypes.c_void_p) if out is not None else None, ctypes.byref(h)))
         dev = DeviceOnsets(self, h, n_rows, wf.shape[1])
         return (dev, out) if return_onsets else dev
+
+    # -- waveform pre-processing (stalta.py:137-211, util.py:479-520) ---------------------------
+    def upload_waveforms(self, waveforms) -> DeviceWaveforms:
+        """``waveforms``: float64 (n_channels, n) raw traces, copied to the device."""
+        wf = np.ascontiguousarray(np.atleast_2d(waveforms), dtype=np.double)
+        h = ctypes.c_void_p()
+        _lib.check(self._lib.qmb_waveforms_upload(self._h, wf, wf.shape[0], wf.shape[1], ctypes.byref(h)))
+        return DeviceWaveforms(self, h, *wf.shape)
+
+    def alloc_waveforms(self, n_channels: int, n: int) -> DeviceWaveforms:
+        h = ctypes.c_void_p()
+        _lib.check(self._lib.qmb_waveforms_alloc(self._h, int(n_channels), int(n), ctypes.byref(h)))
+        return DeviceWaveforms(self, h, n_channels, n)
+
+    def filter_waveforms(self, traces: DeviceWaveforms, sos=None, channels=None, detrend=True,
+                         taper_fraction=0.05, zerophase=True, decimate=1, out=None, out_chan0=0,
+                         timing=False):
+        """
+        detrend (linear + constant) -> cosine taper -> IIR second-order sections (scipy layout,
+        ``(n_sections, 6)``; ``None``: no filter) forward or zero-phase -> every ``decimate``-th
+        sample, for the selected ``channels`` of ``traces`` (default all), written to channels
+        ``out_chan0 ...`` of ``out`` (allocated when ``None``).  Returns ``out`` (and the device
+        time of the kernels in ms when ``timing``).
+        """
+        sel = None if channels is None else np.ascontiguousarray(channels, dtype=np.int32)
+        n_sel = traces.n_channels if sel is None else len(sel)
+        n_out = (traces.n + decimate - 1) // decimate
+        if out is None:
+            out = self.alloc_waveforms(n_sel + out_chan0, n_out)
+        sos_a = None if sos is None else np.ascontiguousarray(np.atleast_2d(sos), dtype=np.double)
+        if sos_a is not None and sos_a.shape[1] != 6:
+            raise ValueError("sos must have shape (n_sections, 6)")
+        ms = ctypes.c_float(0.0)
+        _lib.check(self._lib.qmb_waveforms_filter(
+            self._h, traces._h, None if sel is None else sel.ctypes.data_as(ctypes.c_void_p), int(n_sel),
+            None if sos_a is None else sos_a.ctypes.data_as(ctypes.c_void_p),
+            0 if sos_a is None else sos_a.shape[0], int(bool(detrend)), float(taper_fraction),
+            int(bool(zerophase)), int(decimate), out._h, int(out_chan0),
+            ctypes.cast(ctypes.byref(ms), ctypes.c_void_p) if timing else None))
+        return (out, ms.value) if timing else out
+
+    def preprocess(self, waveforms, sos=None, detrend=True, taper_fraction=0.05, zerophase=True,
+                   decimate=1) -> np.ndarray:
+        """One call, host arrays in and out (``qmb_preprocess``)."""
+        wf = np.ascontiguousarray(np.atleast_2d(waveforms), dtype=np.double)
+        sos_a = None if sos is None else np.ascontiguousarray(np.atleast_2d(sos), dtype=np.double)
+        out = np.empty((wf.shape[0], (wf.shape[1] + decimate - 1) // decimate), dtype=np.double)
+        _lib.check(self._lib.qmb_preprocess(
+            self._h, wf, wf.shape[0], wf.shape[1],
+            None if sos_a is None else sos_a.ctypes.data_as(ctypes.c_void_p),
+            0 if sos_a is None else sos_a.shape[0], int(bool(detrend)), float(taper_fraction),
+            int(bool(zerophase)), int(decimate), out))
+        return out
+
+    def onsets_from_device_waveforms(self, traces: DeviceWaveforms, row_channels, nsta, nlta,
+                                     position="classic", transform="energy", min_onset_value=0.4,
+                                     return_onsets=False):
+        """:meth:`onsets_from_waveforms` on traces that already live on the device."""
+        n_rows = len(row_channels)
+        row_ptr = np.zeros(n_rows + 1, dtype=np.int32)
+        row_ptr[1:] = np.cumsum([len(c) for c in row_channels])
+        row_chan = np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.int32) for c in row_channels]))
+        nsta_a = np.ascontiguousarray(np.broadcast_to(np.asarray(nsta, dtype=np.int32), (n_rows,)))
+        nlta_a = np.ascontiguousarray(np.broadcast_to(np.asarray(nlta, dtype=np.int32), (n_rows,)))
+        out = np.empty((n_rows, traces.n), dtype=np.double) if return_onsets else None
+        h = ctypes.c_void_p()
+        _lib.check(self._lib.qmb_onsets_from_device_waveforms(
+            self._h, traces._h, n_rows, row_ptr, row_chan, nsta_a, nlta_a,
+            _lib.STALTA_POSITION[position], _lib.TRANSFORM[transform], float(min_onset_value),
+            out.ctypes.data_as(ctypes.c_void_p) if out is not None else None, ctypes.byref(h)))
+        dev = DeviceOnsets(self, h, n_rows, traces.n)
+        return (dev, out) if return_onsets else dev
+
+    def envelope(self, signals) -> np.ndarray:
+        """``np.abs(scipy.signal.hilbert(signals, axis=-1))`` (stalta.py:520-523) on the device."""
+        sig = np.ascontiguousarray(np.atleast_2d(signals), dtype=np.double)
+        out = np.empty_like(sig)
+        _lib.check(self._lib.qmb_envelope(self._h, sig, sig.shape[0], sig.shape[1], out))
+        return out
 
     def sta_lta(self, signals, nsta, nlta, position="classic", prefill=None):
         """Batched STA/LTA of (n_channels, n) signals; pre-fill follows lib.py:204,242,281."""

@@ -114,6 +114,8 @@ extern "C" int qmb_ctx_destroy(qmb_ctx_t ctx) {
   ctx->gi2.release(); ctx->gsum.release(); ctx->ex1.release(); ctx->ex2.release(); ctx->gather.release();
   ctx->r_max.release(); ctx->r_norm.release(); ctx->r_idx.release(); ctx->slow_list.release();
   ctx->slow_val.release(); ctx->slow_idx.release(); ctx->flush.release(); ctx->stage_lin.release();
+  ctx->q_i32.release(); ctx->q_f64.release(); ctx->pp_scratch.release(); ctx->pp_sel.release();
+  qmb_fft_release(ctx);
   if (ctx->tmp_onsets) {
     ctx->tmp_onsets->log32.release(); ctx->tmp_onsets->log64.release(); ctx->tmp_onsets->rowmax.release();
     delete ctx->tmp_onsets;
@@ -408,12 +410,14 @@ extern "C" int qmb_onsets_upload(qmb_ctx_t ctx, const double *onsets, int32_t n_
   return QMB_OK;
 }
 
-extern "C" int qmb_onsets_from_waveforms(qmb_ctx_t ctx, const double *waveforms, int32_t n_channels,
-                                         int64_t n_total, int32_t n_rows, const int32_t *row_ptr,
-                                         const int32_t *row_chan, const int32_t *nsta, const int32_t *nlta,
-                                         int32_t position, int32_t transform, double min_onset_value,
-                                         double *onsets_out, qmb_onsets_t *out) {
-  if (!ctx || !waveforms || !row_ptr || !row_chan || !nsta || !nlta || !out) QMB_FAIL(QMB_ERR_ARG, "null argument");
+// `waveforms` is a host array (dev_wf == nullptr) or traces already resident on the device.
+static int onsets_from_traces(qmb_ctx_t ctx, const double *waveforms, const double *dev_wf, int32_t n_channels,
+                              int64_t n_total, int32_t n_rows, const int32_t *row_ptr,
+                              const int32_t *row_chan, const int32_t *nsta, const int32_t *nlta,
+                              int32_t position, int32_t transform, double min_onset_value,
+                              double *onsets_out, qmb_onsets_t *out) {
+  if (!ctx || (!waveforms && !dev_wf) || !row_ptr || !row_chan || !nsta || !nlta || !out)
+    QMB_FAIL(QMB_ERR_ARG, "null argument");
   *out = nullptr;
   if (n_channels <= 0 || n_total <= 0 || n_rows <= 0) QMB_FAIL(QMB_ERR_ARG, "empty input");
   if (position != QMB_STALTA_CLASSIC && position != QMB_STALTA_CENTRED)
@@ -434,7 +438,7 @@ extern "C" int qmb_onsets_from_waveforms(qmb_ctx_t ctx, const double *waveforms,
     if (nlta[r] > max_nlta) max_nlta = nlta[r];
   }
   QMB_CUDA(cudaSetDevice(ctx->device));
-  double *d_wf = nullptr, *d_pair = nullptr, *d_lin = nullptr;
+  double *d_wf = nullptr, *d_pair = nullptr, *d_lin = nullptr, *d_env = nullptr;
   int *d_meta = nullptr;  // [row_ptr (n_rows+1)][row_chan (n_pairs)][nsta (n_pairs)][nlta (n_pairs)]
   const size_t wf_bytes = (size_t)n_channels * n_total * sizeof(double);
   const size_t pair_elems = (size_t)n_pairs * n_total;
@@ -444,6 +448,7 @@ extern "C" int qmb_onsets_from_waveforms(qmb_ctx_t ctx, const double *waveforms,
   auto cleanup = [&]() {
     cudaStreamSynchronize(ctx->stream);
     if (d_wf) cudaFree(d_wf);
+    if (d_env) cudaFree(d_env);
     if (d_pair) cudaFree(d_pair);
     if (d_lin) cudaFree(d_lin);
     if (d_meta) cudaFree(d_meta);
@@ -452,11 +457,20 @@ extern "C" int qmb_onsets_from_waveforms(qmb_ctx_t ctx, const double *waveforms,
   if (rc == QMB_OK) {                           \
     rc = [&]() -> int { expr; return QMB_OK; }(); \
   }
-  QMB_STEP(QMB_CUDA(cudaMalloc((void **)&d_wf, wf_bytes)));
+  if (!dev_wf) QMB_STEP(QMB_CUDA(cudaMalloc((void **)&d_wf, wf_bytes)));
   QMB_STEP(QMB_CUDA(cudaMalloc((void **)&d_pair, pair_elems * sizeof(double))));
   QMB_STEP(QMB_CUDA(cudaMalloc((void **)&d_meta, (size_t)(n_rows + 1 + 3 * n_pairs) * sizeof(int))));
   if (onsets_out) QMB_STEP(QMB_CUDA(cudaMalloc((void **)&d_lin, (size_t)n_rows * n_total * sizeof(double))));
-  QMB_STEP(QMB_CUDA(cudaMemcpyAsync(d_wf, waveforms, wf_bytes, cudaMemcpyHostToDevice, ctx->stream)));
+  if (!dev_wf) QMB_STEP(QMB_CUDA(cudaMemcpyAsync(d_wf, waveforms, wf_bytes, cudaMemcpyHostToDevice, ctx->stream)));
+  const double *d_src = dev_wf ? dev_wf : d_wf;
+  if (transform == QMB_TRANSFORM_ENV || transform == QMB_TRANSFORM_ENV_SQUARED) {
+    // np.abs(hilbert(tr.data)) [** 2] (stalta.py:520-523): envelopes first, then |.| or (.)^2 is
+    // the identity or the energy transform of the STA/LTA kernels
+    QMB_STEP(QMB_CUDA(cudaMalloc((void **)&d_env, wf_bytes)));
+    QMB_STEP(QMB_TRY(qmb_envelope_device(ctx, d_src, n_total, n_channels, n_total, d_env, n_total)));
+    d_src = d_env;
+    transform = transform == QMB_TRANSFORM_ENV ? QMB_TRANSFORM_NONE : QMB_TRANSFORM_ENERGY;
+  }
   int *d_row_ptr = d_meta, *d_row_chan = d_meta ? d_meta + n_rows + 1 : nullptr;
   int *d_nsta = d_meta ? d_row_chan + n_pairs : nullptr, *d_nlta = d_meta ? d_nsta + n_pairs : nullptr;
   QMB_STEP(QMB_CUDA(cudaMemcpyAsync(d_row_ptr, row_ptr, (n_rows + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream)));
@@ -465,7 +479,7 @@ extern "C" int qmb_onsets_from_waveforms(qmb_ctx_t ctx, const double *waveforms,
   QMB_STEP(QMB_CUDA(cudaMemcpyAsync(d_nlta, pair_nlta.data(), n_pairs * sizeof(int), cudaMemcpyHostToDevice, ctx->stream)));
   // pre-fill 1.0 like the reference wrappers (lib.py:204,242), then the valid range
   QMB_STEP(QMB_TRY(qmb_fill_f64(ctx, d_pair, 1.0, pair_elems)));
-  QMB_STEP(QMB_TRY(qmb_stalta_device_ex(ctx, d_wf, n_pairs, n_total, n_total, n_total, max_nsta, max_nlta,
+  QMB_STEP(QMB_TRY(qmb_stalta_device_ex(ctx, d_src, n_pairs, n_total, n_total, n_total, max_nsta, max_nlta,
                                         position, transform, d_pair, d_row_chan, d_nsta, d_nlta)));
   QMB_STEP(QMB_TRY(qmb_onsets_combine(ctx, O, d_pair, n_total, d_row_ptr, min_onset_value, d_lin)));
   if (onsets_out)
@@ -479,6 +493,27 @@ extern "C" int qmb_onsets_from_waveforms(qmb_ctx_t ctx, const double *waveforms,
   }
   *out = O;
   return QMB_OK;
+}
+
+extern "C" int qmb_onsets_from_waveforms(qmb_ctx_t ctx, const double *waveforms, int32_t n_channels,
+                                         int64_t n_total, int32_t n_rows, const int32_t *row_ptr,
+                                         const int32_t *row_chan, const int32_t *nsta, const int32_t *nlta,
+                                         int32_t position, int32_t transform, double min_onset_value,
+                                         double *onsets_out, qmb_onsets_t *out) {
+  if (!waveforms) QMB_FAIL(QMB_ERR_ARG, "null argument");
+  return onsets_from_traces(ctx, waveforms, nullptr, n_channels, n_total, n_rows, row_ptr, row_chan, nsta, nlta,
+                            position, transform, min_onset_value, onsets_out, out);
+}
+
+extern "C" int qmb_onsets_from_device_waveforms(qmb_ctx_t ctx, qmb_waveforms_t w, int32_t n_rows,
+                                                const int32_t *row_ptr, const int32_t *row_chan,
+                                                const int32_t *nsta, const int32_t *nlta, int32_t position,
+                                                int32_t transform, double min_onset_value,
+                                                double *onsets_out, qmb_onsets_t *out) {
+  if (!ctx || !w) QMB_FAIL(QMB_ERR_ARG, "null argument");
+  if (w->ctx != ctx) QMB_FAIL(QMB_ERR_ARG, "handles belong to a different context");
+  return onsets_from_traces(ctx, nullptr, w->data.p, w->C, w->n, n_rows, row_ptr, row_chan, nsta, nlta,
+                            position, transform, min_onset_value, onsets_out, out);
 }
 
 extern "C" int qmb_sta_lta(qmb_ctx_t ctx, const double *signal, int32_t n_channels, int64_t n, int32_t nsta,

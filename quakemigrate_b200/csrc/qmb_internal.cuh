@@ -118,6 +118,12 @@ struct qmb_ctx {
   DevBuf<double> stage_lin;     // H2D staging of linear onsets (reused across calls)
   DevBuf<int32_t> q_i32;        // output stage: quantised channels + unravelled indices
   DevBuf<double> q_f64;         // output stage: grid coordinates
+  DevBuf<double> pp_scratch;    // pre-processing: stats, matrix powers, chunk/tile states, pass-1 output
+  DevBuf<int> pp_sel;           // pre-processing: selected channel indices
+  // Hilbert envelopes: cached cuFFT plan pair (handles are ints) and complex scratch
+  int fft_fwd = 0, fft_inv = 0, fft_batch = 0;
+  int64_t fft_n = 0, fft_idist = 0;
+  DevBuf<double> fft_buf;
   struct qmb_onsets *tmp_onsets = nullptr;  // onset rows of the one-call qmb_detect (reused)
   int32_t last_n_samples = 0;
   // pinned staging for small D2H
@@ -161,6 +167,14 @@ struct qmb_onsets {
   DevBuf<double> rowmax;  // [S] max |log onset| per row (for the fp32 error bound)
 };
 
+struct qmb_waveforms {  // device-resident float64 traces, (C, n) C-order
+  qmb_ctx *ctx = nullptr;
+  int device = 0;
+  int32_t C = 0;
+  int64_t n = 0;
+  DevBuf<double> data;
+};
+
 constexpr int64_t QMB_ONSET_FRONT = 4;     // leading pad (elements); alignment slack
 constexpr int64_t QMB_ONSET_TAIL = 1024;   // trailing zero pad: >= time tile + max tile span + 8
 
@@ -192,4 +206,11 @@ int qmb_onsets_combine(qmb_ctx *ctx, qmb_onsets *O, const double *d_chan, int64_
                        const int *d_row_ptr, double min_onset, double *d_lin_out);
 int qmb_nccl_allgather(qmb_ctx *ctx, const void *send, void *recv, size_t bytes_per_rank);
 int qmb_nccl_allreduce_sum_f64(qmb_ctx *ctx, double *buf, size_t count);
+int qmb_preprocess_device(qmb_ctx *ctx, const double *d_x, int64_t x_stride, const int *d_chan_in,
+                          int32_t n_sel, int64_t n, const double *sos, int32_t nsec, int32_t detrend,
+                          double taper_fraction, int32_t zerophase, int32_t decimate, double *d_out,
+                          int64_t out_stride, int32_t out_chan0, float *kernel_ms);
+int qmb_envelope_device(qmb_ctx *ctx, const double *d_x, int64_t x_stride, int32_t n_channels, int64_t n,
+                        double *d_out, int64_t out_stride);
+void qmb_fft_release(qmb_ctx *ctx);
 qmb_ctx *qmb_default_ctx();

@@ -10,8 +10,10 @@ against ``quakemigrate.signal.onsets`` keeps working:
   ``device_onsets`` handle so that the scan can skip a second host->device copy.
 * :class:`STALTAOnset` -- the default onset (``quakemigrate/signal/onsets/stalta.py:214-635``)
   with the per-channel STA/LTA, RMS combine and clip running on the GPU
-  (``qmb_onsets_from_waveforms``).  Filtering / resampling (``stalta.py:137-211``, obspy) is
-  upstream of the hot path and out of scope: waveforms arrive pre-processed.
+  (``qmb_onsets_from_waveforms``).  With ``bandpass_filters`` the pre-processing of
+  ``stalta.py:137-211`` (detrend, taper, zero-phase Butterworth band-pass per phase) also runs on
+  the device and the filtered traces feed the STA/LTA kernels without a host round trip;
+  without it, waveforms are taken as already pre-processed.
 
 Waveform containers are duck-typed: anything with ``stations``, ``starttime``, ``endtime`` and
 ``channels`` (dict ``station -> {component letter -> 1-D float array}``) works;
@@ -95,6 +97,24 @@ class OnsetData:
         self.device_onsets = device_onsets
 
 
+class FilteredWaveforms:
+    """
+    The pre-processed traces of an onset calculation (``OnsetData.filtered_waveforms``; the
+    reference keeps an obspy Stream, stalta.py:470), left on the device and copied out on demand:
+    the picker and the plots want them, detect() never does.
+    """
+
+    def __init__(self, device_waveforms, index):
+        self.device, self.index = device_waveforms, index  # {(station, component, phase): row}
+
+    def trace(self, station, component, phase):
+        return self.device.fetch(self.index[(station, component, phase)], 1)[0]
+
+    def to_host(self):
+        block = self.device.fetch()
+        return {key: block[i] for key, i in self.index.items()}
+
+
 class WaveformData:
     """Minimal stand-in for ``quakemigrate.io.data.WaveformData`` (pre-processed data only)."""
 
@@ -121,7 +141,11 @@ class STALTAOnset(Onset):
     Keyword arguments follow the reference (stalta.py:214-350): ``position`` ("classic" |
     "centred"), ``phases``, ``sta_lta_windows`` ({phase: [sta_s, lta_s]}), ``channel_maps``
     ({phase: component letters, e.g. {"P": "Z", "S": "NE"}}), ``signal_transform``
-    ("energy" | "abs"), ``min_onset_value`` (default 0.4), ``all_channels``.
+    ("energy" | "abs" | "env" | "env_squared"; the envelopes are ``|hilbert(x)|`` via batched FFTs
+    on the device), ``min_onset_value`` (default 0.4), ``all_channels``, and
+    ``bandpass_filters`` ({phase: [lowcut_hz, highcut_hz, corners]}, stalta.py:279-283).  The
+    reference always filters; here ``bandpass_filters=None`` (default) means "the container holds
+    pre-processed traces", anything else runs ``pre_process`` on the device first.
     """
 
     def __init__(self, engine=None, **kwargs):
@@ -134,13 +158,17 @@ class STALTAOnset(Onset):
         self.sta_lta_windows = kwargs.get("sta_lta_windows", {"P": [0.2, 1.0], "S": [0.2, 1.0]})
         self.channel_maps = kwargs.get("channel_maps", {"P": "Z", "S": "NE"})
         self.signal_transform = kwargs.get("signal_transform", "energy")
-        if self.signal_transform not in ("energy", "abs"):
-            raise NotImplementedError(
-                "signal_transform 'env'/'env_squared' need the Hilbert transform, which belongs "
-                "to the (out-of-scope) pre-processing stage; pass envelopes with transform 'abs'"
-            )
+        if self.signal_transform not in ("energy", "abs", "env", "env_squared"):  # stalta.py:516-523
+            raise ValueError(f"unknown signal_transform {self.signal_transform!r}")
         self.min_onset_value = kwargs.get("min_onset_value", 0.4)
         self.all_channels = kwargs.get("all_channels", False)
+        self.bandpass_filters = kwargs.get("bandpass_filters", None)
+        if self.bandpass_filters is not None:
+            from .preprocess import NyquistException
+            for phase in self.phases:
+                _, highcut, _ = self.bandpass_filters[phase]
+                if highcut >= 0.5 * self.sampling_rate:  # stalta.py:198-199
+                    raise NyquistException(highcut, 0.5 * self.sampling_rate, "")
 
     def __str__(self):
         out = (f"\tOnset parameters - using the {self.position} STA/LTA onset (GPU)"
@@ -182,6 +210,7 @@ class STALTAOnset(Onset):
         n_total = None
         availability, rows, chan_arrays = {}, [], []
         chan_index = {}
+        per_phase = self.bandpass_filters is not None  # filtered traces are specific to a phase
         for phase in self.phases:
             comps = self.channel_maps[phase]
             stw, ltw = self.sta_lta_windows[phase]
@@ -201,13 +230,40 @@ class STALTAOnset(Onset):
                     continue
                 idxs = []
                 for c in have:
-                    key = (station, c)
+                    key = (station, c, phase) if per_phase else (station, c)
                     if key not in chan_index:
                         chan_index[key] = len(chan_arrays)
                         chan_arrays.append(np.asarray(data.channels[station][c], dtype=np.double))
                     idxs.append(chan_index[key])
                 rows.append((station, phase, idxs, nsta, nlta))
+        self._last_chan_index = chan_index
         return availability, rows, chan_arrays
+
+    def _filter_on_device(self, waveforms, chan_index):
+        """``pre_process`` (stalta.py:203-209) per phase; returns the filtered DeviceWaveforms."""
+        from .preprocess import butter_sos
+
+        raw = self.engine.upload_waveforms(waveforms)
+        try:
+            filtered = self.engine.alloc_waveforms(*raw.shape)
+            for phase in self.phases:
+                sel = [i for key, i in chan_index.items() if key[2] == phase]
+                if not sel:
+                    continue
+                lowcut, highcut, corners = self.bandpass_filters[phase]
+                sos = butter_sos("bandpass", (lowcut, highcut), self.sampling_rate, corners)
+                # channels of one phase are contiguous in first-seen order: filter them in runs
+                start = 0
+                while start < len(sel):
+                    stop = start + 1
+                    while stop < len(sel) and sel[stop] == sel[stop - 1] + 1:
+                        stop += 1
+                    self.engine.filter_waveforms(raw, sos, channels=sel[start:stop], out=filtered,
+                                                 out_chan0=sel[start])
+                    start = stop
+            return filtered
+        finally:
+            raw.free()
 
     def calculate_onsets(self, data, timespan=None):
         """
@@ -222,10 +278,19 @@ class STALTAOnset(Onset):
         if sum(availability.values()) == 0:
             raise DataAvailabilityException
         waveforms = np.stack(chan_arrays, axis=0)
-        dev, onsets = self.engine.onsets_from_waveforms(
-            waveforms, [r[2] for r in rows], [r[3] for r in rows], [r[4] for r in rows],
-            position=self.position, transform=self.signal_transform,
-            min_onset_value=self.min_onset_value, return_onsets=True)
+        filtered_waveforms = data.channels
+        if self.bandpass_filters is not None:
+            filtered = self._filter_on_device(waveforms, self._last_chan_index)
+            dev, onsets = self.engine.onsets_from_device_waveforms(
+                filtered, [r[2] for r in rows], [r[3] for r in rows], [r[4] for r in rows],
+                position=self.position, transform=self.signal_transform,
+                min_onset_value=self.min_onset_value, return_onsets=True)
+            filtered_waveforms = FilteredWaveforms(filtered, dict(self._last_chan_index))
+        else:
+            dev, onsets = self.engine.onsets_from_waveforms(
+                waveforms, [r[2] for r in rows], [r[3] for r in rows], [r[4] for r in rows],
+                position=self.position, transform=self.signal_transform,
+                min_onset_value=self.min_onset_value, return_onsets=True)
         if timespan:
             # _trim_taper_pad (stalta.py:550-584): the tapered pre-/post-pad plus one LTA / STA
             # window is set to 1 on every channel before the RMS combine; every channel of a row
@@ -242,6 +307,6 @@ class STALTAOnset(Onset):
         onsets_dict = {}
         for i, (station, phase, _, _, _) in enumerate(rows):
             onsets_dict.setdefault(station, {})[phase] = onsets[i]
-        onset_data = OnsetData(onsets_dict, self.phases, self.channel_maps, data.channels, availability,
+        onset_data = OnsetData(onsets_dict, self.phases, self.channel_maps, filtered_waveforms, availability,
                                data.starttime, data.endtime, self.sampling_rate, device_onsets=dev)
         return onsets, onset_data
