@@ -95,6 +95,28 @@ class LUT(Grid3D):
                     traveltimes.append(self[station][f"TIME_{phase}"])
         return np.stack(traveltimes, axis=-1)
 
+    def decimate(self, df, inplace=False):
+        """
+        lut.py:102-140: keep every ``df``-th node per axis, starting ``c1`` nodes in so that the
+        kept nodes are centred.  Like the reference, ``node_spacing`` is scaled and ``ll_corner``
+        is left as it is (the reference does not shift it by ``c1 * node_spacing``).
+        """
+        import copy
+
+        df = np.array(df, dtype=int)
+        new_node_count = 1 + (self.node_count - 1) // df
+        c1 = (self.node_count - df * (new_node_count - 1) - 1) // 2
+        grid = self if inplace else copy.copy(self)
+        if not inplace:
+            grid.traveltimes = {st: dict(m) for st, m in self.traveltimes.items()}
+        grid.node_count = new_node_count
+        grid.node_spacing = self.node_spacing * df
+        for station, map_ in grid.traveltimes.items():
+            for phase, ttimes in map_.items():
+                map_[phase] = ttimes[c1[0]::df[0], c1[1]::df[1], c1[2]::df[2]]
+        if not inplace:
+            return grid
+
     @property
     def max_traveltime(self):
         """lut.py:842-845."""

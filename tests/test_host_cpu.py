@@ -167,3 +167,25 @@ def test_sharded_merge_world2_gloo(tmp_path):
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+
+
+def test_lut_decimate_matches_reference_slicing():
+    """LUT.decimate (lut/lut.py:102-140): node count, spacing and the centred start offset."""
+    from quakemigrate_b200.lut import LUT
+
+    rng = np.random.default_rng(5)
+    shape = (11, 8, 7)
+    tts = {f"S{k}": {"P": rng.random(shape), "S": rng.random(shape)} for k in range(3)}
+    lut = LUT(tts, shape, (0.5, 0.5, 0.25), (1.0, 2.0, -3.0))
+    dec = lut.decimate([2, 3, 2])
+    assert list(dec.node_count) == [6, 3, 4] and list(lut.node_count) == [11, 8, 7]
+    np.testing.assert_allclose(dec.node_spacing, [1.0, 1.5, 0.5])
+    np.testing.assert_allclose(dec.ll_corner, lut.ll_corner)  # the reference leaves it untouched
+    # c1 = (n - df * (new - 1) - 1) // 2 = (0, 0, 0) for x, (8 - 6 - 1) // 2 = 0 for y, 0 for z
+    np.testing.assert_array_equal(dec["S1"]["S"], tts["S1"]["S"][0::2, 0::3, 0::2])
+    dec2 = lut.decimate([4, 4, 4])
+    # x: new = 3, c1 = (11 - 8 - 1) // 2 = 1;  y: new = 2, c1 = (8 - 4 - 1) // 2 = 1;  z: new = 2, c1 = 1
+    np.testing.assert_array_equal(dec2["S0"]["P"], tts["S0"]["P"][1::4, 1::4, 1::4])
+    assert dec2.serve_traveltimes(50).shape == (3, 2, 2, 6)
+    lut.decimate([2, 2, 2], inplace=True)
+    assert list(lut.node_count) == [6, 4, 4] and lut["S2"]["P"].shape == (6, 4, 4)
