@@ -10,11 +10,13 @@
 // A recursive (IIR) filter is a serial recurrence in time, but it is LINEAR: the state at the end
 // of a span is  M^len * state_in + (state reached from zero).  So time is cut into chunks of
 // PP_L samples, one thread each:
+//   k_pre_partial / k_pre_stats  mean and least-squares slope of every trace (tile partial sums,
+//                folded in a fixed order);
 //   k_sos_state  every chunk is filtered from a ZERO state (input staged through shared memory,
 //                detrend + taper applied on the fly); a Hillis-Steele scan over the tile's
 //                PP_TPB chunks with the pre-computed powers M^1, M^2, M^4 ... turns the per-chunk
 //                end states into "state at chunk start, given zero state at tile start";
-//   k_sos_carry  one thread per trace chains the tiles: in[T+1] = M^PP_TPB * in[T] + end[T];
+//   k_sos_carry  one warp per trace chains the tiles: in[T+1] = M^PP_TPB * in[T] + end[T];
 //   k_sos_apply  every chunk is filtered again, now from its TRUE initial state
 //                (chunk_state + M^t * tile_in), i.e. with the very operation sequence of scipy's
 //                sosfilt (direct form II transposed, section by section); output through shared
@@ -89,44 +91,58 @@ __device__ __forceinline__ double pre_sample(const PreParams &p, double v, long 
 
 // Stage tile T of selection s in shared memory, in PROCESSING order q (q-th processed sample is
 // x[q] forward, x[n-1-q] backward); chunk t occupies tile[t * (PP_L + 1) .. + PP_L).
+// All PP_L loads of a thread are issued before the first use (one DRAM latency per tile, not 32).
 template <bool REV>
 __device__ __forceinline__ void load_tile(const PreParams &p, double *tile, int T, int s) {
   const int ch = p.chan_in ? p.chan_in[s] : s;
-  const double *x = p.x + (size_t)ch * p.x_stride;
-  double mean = 0.0, slope = 0.0;
+  const double *__restrict__ x = p.x + (size_t)ch * p.x_stride;
+  const long long q0 = (long long)T * PP_TILE + threadIdx.x;
+  double v[PP_L];
+#pragma unroll
+  for (int j = 0; j < PP_L; ++j) {
+    const long long q = q0 + (long long)j * PP_TPB;
+    v[j] = q < p.n ? __ldg(x + (REV ? p.n - 1 - q : q)) : 0.0;
+  }
   if (p.apply_pre) {
-    mean = p.stats[2 * s];
-    slope = p.stats[2 * s + 1];
-  }
-  for (int k = threadIdx.x; k < PP_TILE; k += PP_TPB) {
-    const long long q = (long long)T * PP_TILE + k;
-    double v = 0.0;
-    if (q < p.n) {
-      const long long i = REV ? p.n - 1 - q : q;
-      v = x[i];
-      if (p.apply_pre) v = pre_sample(p, v, i, mean, slope);
+    const double mean = p.stats[2 * s], slope = p.stats[2 * s + 1];
+#pragma unroll
+    for (int j = 0; j < PP_L; ++j) {
+      const long long q = q0 + (long long)j * PP_TPB;
+      if (q < p.n) v[j] = pre_sample(p, v[j], REV ? p.n - 1 - q : q, mean, slope);
     }
-    tile[k + k / PP_L] = v;
   }
+  // k = threadIdx.x + j * PP_TPB  ->  k / PP_L = threadIdx.x / PP_L + j * (PP_TPB / PP_L)
+  double *dst = tile + threadIdx.x + threadIdx.x / PP_L;
+#pragma unroll
+  for (int j = 0; j < PP_L; ++j) dst[j * (PP_TPB + PP_TPB / PP_L)] = v[j];
 }
 
-// ---- per-trace mean and slope (least-squares line), one CTA per selected trace -----------------
-__global__ void __launch_bounds__(1024) k_pre_moments(PreParams p, double *stats, int detrend) {
-  const int s = blockIdx.x;
+// ---- per-trace mean and slope (least-squares line) ------------------------------------------------
+// k_pre_partial: one CTA per tile, sum x and sum (i - tbar) x of its 8192 samples -> partial[s][T][2]
+// k_pre_stats  : one warp per trace folds the partials in a fixed order (deterministic)
+__global__ void __launch_bounds__(PP_TPB) k_pre_partial(PreParams p, double *partial) {
+  const int T = blockIdx.x, s = blockIdx.y;
   const int ch = p.chan_in ? p.chan_in[s] : s;
-  const double *x = p.x + (size_t)ch * p.x_stride;
+  const double *__restrict__ x = p.x + (size_t)ch * p.x_stride;
+  const long long q0 = (long long)T * PP_TILE + threadIdx.x;
+  double v[PP_L];
+#pragma unroll
+  for (int j = 0; j < PP_L; ++j) {
+    const long long q = q0 + (long long)j * PP_TPB;
+    v[j] = q < p.n ? __ldg(x + q) : 0.0;
+  }
   double s0 = 0.0, s1 = 0.0;
-  if (detrend)
-    for (long long i = threadIdx.x; i < p.n; i += blockDim.x) {
-      const double v = x[i];
-      s0 += v;
-      s1 += ((double)i - p.tbar) * v;
-    }
+#pragma unroll
+  for (int j = 0; j < PP_L; ++j) {
+    const long long q = q0 + (long long)j * PP_TPB;
+    s0 += v[j];
+    s1 += ((double)q - p.tbar) * v[j];
+  }
   for (int o = 16; o > 0; o >>= 1) {
     s0 += __shfl_xor_sync(0xffffffffu, s0, o);
     s1 += __shfl_xor_sync(0xffffffffu, s1, o);
   }
-  __shared__ double w0[32], w1[32];
+  __shared__ double w0[PP_TPB / 32], w1[PP_TPB / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) {
     w0[warp] = s0;
@@ -136,10 +152,28 @@ __global__ void __launch_bounds__(1024) k_pre_moments(PreParams p, double *stats
   if (threadIdx.x == 0) {
     s0 = 0.0;
     s1 = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+    for (int w = 0; w < PP_TPB / 32; ++w) {
       s0 += w0[w];
       s1 += w1[w];
     }
+    partial[2 * ((size_t)s * p.ntiles + T)] = s0;
+    partial[2 * ((size_t)s * p.ntiles + T) + 1] = s1;
+  }
+}
+
+__global__ void __launch_bounds__(32) k_pre_stats(PreParams p, const double *partial, double *stats, int detrend) {
+  const int s = blockIdx.x, lane = threadIdx.x;
+  double s0 = 0.0, s1 = 0.0;
+  if (detrend)
+    for (int T = lane; T < p.ntiles; T += 32) {
+      s0 += partial[2 * ((size_t)s * p.ntiles + T)];
+      s1 += partial[2 * ((size_t)s * p.ntiles + T) + 1];
+    }
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  }
+  if (lane == 0) {
     const double nn = (double)p.n;
     const double sxx = nn * (nn * nn - 1.0) / 12.0;  // sum (i - tbar)^2
     stats[2 * s] = detrend ? s0 / nn : 0.0;
@@ -201,29 +235,42 @@ __global__ void __launch_bounds__(PP_TPB) k_sos_state(PreParams p) {
 }
 
 // ---- pass 2: chain the tiles of each trace --------------------------------------------------------
+// One warp per trace.  32 tile end states at a time are loaded side by side into shared memory
+// (one global latency per 32 tiles instead of one per tile), lane 0 runs the short recurrence, and
+// the 32 incoming states go out side by side again.
 template <int NSEC>
 __global__ void __launch_bounds__(32) k_sos_carry(PreParams p) {
   constexpr int D = 2 * NSEC;
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= p.n_sel) return;
-  const double *M = p.mpow + (size_t)PP_TPB * D * D;
+  __shared__ double zs[32 * D], ins[32 * D], Ms[D * D];
+  const int s = blockIdx.x, lane = threadIdx.x;
+  for (int i = lane; i < D * D; i += 32) Ms[i] = p.mpow[(size_t)PP_TPB * D * D + i];
   double cur[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) cur[d] = 0.0;
-  for (int T = 0; T < p.ntiles; ++T) {
-    double *tin = p.tile_in + ((size_t)s * p.ntiles + T) * D;
-    const double *z = p.tile_state + ((size_t)s * p.ntiles + T) * D;
-    double nx[D];
+  for (int T0 = 0; T0 < p.ntiles; T0 += 32) {
+    const int cnt = min(32, p.ntiles - T0);
+    const double *z = p.tile_state + ((size_t)s * p.ntiles + T0) * D;
+    for (int i = lane; i < cnt * D; i += 32) zs[i] = z[i];
+    __syncwarp();
+    if (lane == 0) {
+      for (int k = 0; k < cnt; ++k) {
+        double nx[D];
 #pragma unroll
-    for (int i = 0; i < D; ++i) {
-      tin[i] = cur[i];
-      double acc = z[i];
+        for (int i = 0; i < D; ++i) {
+          ins[k * D + i] = cur[i];
+          double acc = zs[k * D + i];
 #pragma unroll
-      for (int j = 0; j < D; ++j) acc += M[i * D + j] * cur[j];
-      nx[i] = acc;
+          for (int j = 0; j < D; ++j) acc += Ms[i * D + j] * cur[j];
+          nx[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) cur[i] = nx[i];
+      }
     }
-#pragma unroll
-    for (int i = 0; i < D; ++i) cur[i] = nx[i];
+    __syncwarp();
+    double *tin = p.tile_in + ((size_t)s * p.ntiles + T0) * D;
+    for (int i = lane; i < cnt * D; i += 32) tin[i] = ins[i];
+    __syncwarp();
   }
 }
 
@@ -312,7 +359,7 @@ int run_pass(qmb_ctx *ctx, PreParams &p, bool rev) {
     k_sos_state<NSEC, false><<<grid, PP_TPB, smem_state, ctx->stream>>>(p);
   }
   QMB_CUDA(cudaGetLastError());
-  k_sos_carry<NSEC><<<(p.n_sel + 31) / 32, 32, 0, ctx->stream>>>(p);
+  k_sos_carry<NSEC><<<p.n_sel, 32, 0, ctx->stream>>>(p);
   QMB_CUDA(cudaGetLastError());
   if (rev) k_sos_apply<NSEC, true><<<grid, PP_TPB, smem_apply, ctx->stream>>>(p);
   else k_sos_apply<NSEC, false><<<grid, PP_TPB, smem_apply, ctx->stream>>>(p);
@@ -364,8 +411,8 @@ int qmb_preprocess_device(qmb_ctx *ctx, const double *d_x, int64_t x_stride, con
     p.coef[5 * k + 3] = sos[6 * k + 4] / a0;
     p.coef[5 * k + 4] = sos[6 * k + 5] / a0;
   }
-  // scratch: stats | mpow | chunk_state | tile_state | tile_in | forward output
-  const size_t n_stats = (size_t)2 * n_sel;
+  // scratch: stats | partial sums | mpow | chunk_state | tile_state | tile_in | forward output
+  const size_t n_stats = (size_t)2 * n_sel + (size_t)2 * n_sel * p.ntiles;
   const size_t n_mpow = (size_t)(PP_TPB + 1) * D * D;
   const size_t n_chunk = (size_t)n_sel * p.ntiles * PP_TPB * D;
   const size_t n_tile = (size_t)n_sel * p.ntiles * D;
@@ -399,7 +446,13 @@ int qmb_preprocess_device(qmb_ctx *ctx, const double *d_x, int64_t x_stride, con
     QMB_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   if (kernel_ms) QMB_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-  k_pre_moments<<<n_sel, 1024, 0, ctx->stream>>>(p, d_stats, detrend ? 1 : 0);
+  double *d_partial = d_stats + (size_t)2 * n_sel;
+  if (detrend) {
+    k_pre_partial<<<dim3((unsigned)p.ntiles, (unsigned)n_sel), PP_TPB, 0, ctx->stream>>>(p, d_partial);
+    ctx->launches++;
+    QMB_CUDA(cudaGetLastError());
+  }
+  k_pre_stats<<<n_sel, 32, 0, ctx->stream>>>(p, d_partial, d_stats, detrend ? 1 : 0);
   ctx->launches++;
   QMB_CUDA(cudaGetLastError());
   p.apply_pre = 1;
