@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--variant", type=int, default=-1, help="kernel tiling variant id; -1 = library default")
     ap.add_argument("--samples", type=int, default=0, help="override n_samples (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pre-only", action="store_true",
+                    help="profiling aid: run only the pre-processing stage on the workload's full-length traces")
     ap.add_argument("--strong", action="store_true",
                     help="strong scaling: shard the FIXED workload grid over the ranks (default: weak, one "
                          "workload-sized slab per GPU)")
@@ -273,6 +275,11 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
     P = prob.n_total
 
     eng = Engine(local_rank, variant=args.variant if args.variant >= 0 else None)
+    if args.pre_only:
+        full = syn.make_problem(global_config(base, 1, 0), with_waveforms=True)
+        print(json.dumps(preprocess_stage(eng, base, full, args, *measured_peak_hbm())), flush=True)
+        eng.close()
+        return
     if world > 1:
         ids = [Engine.new_comm_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0, group=CTRL_GROUP)

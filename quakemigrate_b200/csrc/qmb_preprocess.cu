@@ -73,25 +73,31 @@ __device__ __forceinline__ double cascade_step(const double *c, double (&s)[2 * 
   return x;
 }
 
-// detrend("linear") + detrend("constant") + cosine taper of sample i
+// cosine taper weight of sample i (obspy Trace.taper(type="cosine") with wlen samples per side)
+__device__ __noinline__ double taper_weight(long long i, long long n, long long wlen) {
+  const long long w1 = wlen - 1;
+  if (i < wlen)  // 0.5 * (1 - cos(pi * k / (wlen - 1))), k = i
+    return w1 > 0 ? 0.5 * (1.0 - cos(PP_PI * (double)i / (double)w1)) : 0.0;
+  if (i >= n - wlen) {  // 0.5 * (1 + cos(pi * j / (wlen - 1))), j = i - (n - wlen)
+    const long long j = i - (n - wlen);
+    return w1 > 0 ? 0.5 * (1.0 + cos(PP_PI * (double)j / (double)w1)) : 0.0;
+  }
+  return 1.0;
+}
+
+// detrend("linear") + detrend("constant") + cosine taper of sample i (element-wise kernels)
 __device__ __forceinline__ double pre_sample(const PreParams &p, double v, long long i, double mean,
                                              double slope) {
   v -= mean + slope * ((double)i - p.tbar);
-  if (p.wlen > 0) {
-    const long long w1 = p.wlen - 1;
-    if (i < p.wlen) {  // 0.5 * (1 - cos(pi * k / (wlen - 1))), k = i
-      v *= w1 > 0 ? 0.5 * (1.0 - cos(PP_PI * (double)i / (double)w1)) : 0.0;
-    } else if (i >= p.n - p.wlen) {  // 0.5 * (1 + cos(pi * j / (wlen - 1))), j = i - (n - wlen)
-      const long long j = i - (p.n - p.wlen);
-      v *= w1 > 0 ? 0.5 * (1.0 + cos(PP_PI * (double)j / (double)w1)) : 0.0;
-    }
-  }
+  if (p.wlen > 0 && (i < p.wlen || i >= p.n - p.wlen)) v *= taper_weight(i, p.n, p.wlen);
   return v;
 }
 
 // Stage tile T of selection s in shared memory, in PROCESSING order q (q-th processed sample is
 // x[q] forward, x[n-1-q] backward); chunk t occupies tile[t * (PP_L + 1) .. + PP_L).
-// All PP_L loads of a thread are issued before the first use (one DRAM latency per tile, not 32).
+// All PP_L loads of a thread are issued before the first use (one DRAM latency per tile, not 32);
+// the line is removed in registers; the taper touches only the tiles at either end of the trace
+// (CTA-uniform branch, rolled loop: the cosine code exists once).
 template <bool REV>
 __device__ __forceinline__ void load_tile(const PreParams &p, double *tile, int T, int s) {
   const int ch = p.chan_in ? p.chan_in[s] : s;
@@ -103,18 +109,36 @@ __device__ __forceinline__ void load_tile(const PreParams &p, double *tile, int 
     const long long q = q0 + (long long)j * PP_TPB;
     v[j] = q < p.n ? __ldg(x + (REV ? p.n - 1 - q : q)) : 0.0;
   }
+  // k = threadIdx.x + j * PP_TPB  ->  k / PP_L = threadIdx.x / PP_L + j * (PP_TPB / PP_L)
+  double *dst = tile + threadIdx.x + threadIdx.x / PP_L;
+  constexpr int STEP = PP_TPB + PP_TPB / PP_L;
   if (p.apply_pre) {
-    const double mean = p.stats[2 * s], slope = p.stats[2 * s + 1];
+    const double slope = p.stats[2 * s + 1];
+    const double step = REV ? -(double)PP_TPB : (double)PP_TPB;
+    // value of the fitted line at this thread's first sample; later samples are +-PP_TPB apart
+    const double line0 = p.stats[2 * s] + slope * ((double)(REV ? p.n - 1 - q0 : q0) - p.tbar);
 #pragma unroll
     for (int j = 0; j < PP_L; ++j) {
       const long long q = q0 + (long long)j * PP_TPB;
-      if (q < p.n) v[j] = pre_sample(p, v[j], REV ? p.n - 1 - q : q, mean, slope);
+      if (q < p.n) v[j] -= line0 + slope * (step * (double)j);
     }
   }
-  // k = threadIdx.x + j * PP_TPB  ->  k / PP_L = threadIdx.x / PP_L + j * (PP_TPB / PP_L)
-  double *dst = tile + threadIdx.x + threadIdx.x / PP_L;
 #pragma unroll
-  for (int j = 0; j < PP_L; ++j) dst[j * (PP_TPB + PP_TPB / PP_L)] = v[j];
+  for (int j = 0; j < PP_L; ++j) dst[j * STEP] = v[j];
+  if (p.apply_pre && p.wlen > 0) {
+    // samples of this tile: processing positions [qa, qb] <-> trace indices [lo, hi]
+    const long long qa = (long long)T * PP_TILE, qb = min(qa + PP_TILE, p.n) - 1;
+    const long long lo = REV ? p.n - 1 - qb : qa, hi = REV ? p.n - 1 - qa : qb;
+    if (lo < p.wlen || hi >= p.n - p.wlen) {
+#pragma unroll 1
+      for (int j = 0; j < PP_L; ++j) {
+        const long long q = q0 + (long long)j * PP_TPB;
+        if (q >= p.n) break;
+        const long long i = REV ? p.n - 1 - q : q;
+        if (i < p.wlen || i >= p.n - p.wlen) dst[j * STEP] *= taper_weight(i, p.n, p.wlen);
+      }
+    }
+  }
 }
 
 // ---- per-trace mean and slope (least-squares line) ------------------------------------------------

@@ -14,7 +14,7 @@ timeout 150 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
 for extra in "$@"; do
   case $extra in
     cfg3pre) timeout 200 python scripts/preprocess_bench.py > gpurun_out/preprocess_cfg3.json 2> gpurun_out/preprocess_cfg3.err; cat gpurun_out/preprocess_cfg3.json; tail -3 gpurun_out/preprocess_cfg3.err;;
-    full) timeout 150 ncu --set full --clock-control none --import-source on -k regex:k_sos_apply -s 4 -c 2 -o gpurun_out/prof_sos_apply python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_c.log 2>&1;;
+    full) timeout 150 ncu --set full --clock-control none --import-source on -k regex:"k_sos_state|k_sos_apply" -c 4 -o gpurun_out/prof_sos python bench.py --steps 1 --warmup 1 --samples 12000 --no-cpu-baseline --pre-only > gpurun_out/ncu_full_c.log 2>&1;;
   esac
 done
 ls -la gpurun_out | tail -12
