@@ -54,6 +54,8 @@ def parse_args():
     ap.add_argument("--workload", default="cfg2", choices=sorted(syn.CONFIGS))
     ap.add_argument("--variant", type=int, default=-1, help="kernel tiling variant id; -1 = library default")
     ap.add_argument("--samples", type=int, default=0, help="override n_samples (debug)")
+    ap.add_argument("--precision", default=None, choices=["q16", "fp32"],
+                    help="operand format of the scan's gathers (library default: q16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pre-only", action="store_true",
                     help="profiling aid: run only the pre-processing stage on the workload's full-length traces")
@@ -274,7 +276,7 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
     N_global, T, S = cfg.n_nodes, cfg.n_samples, cfg.n_rows
     P = prob.n_total
 
-    eng = Engine(local_rank, variant=args.variant if args.variant >= 0 else None)
+    eng = Engine(local_rank, variant=args.variant if args.variant >= 0 else None, precision=args.precision)
     if args.pre_only:
         full = syn.make_problem(global_config(base, 1, 0), with_waveforms=True)
         print(json.dumps(preprocess_stage(eng, base, full, args, *measured_peak_hbm())), flush=True)
@@ -356,6 +358,9 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     ga = float(N_local) * T * S / (scan_mean * 1e-3)
     smem_peak = 148 * 32 * sm_mhz * 1e6
+    # shared-memory bytes one gathered operand costs: 4 (float32 rows) or 2 (16-bit fixed-point
+    # rows, two samples per LDS.32); the pipe moves 128 B/clk/SM either way
+    bpg = eng.last_scan_bytes_per_gather
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -370,6 +375,7 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
             "parallelism": f"node-slab x{world}", "cache": "L2 flushed (256 MiB memset) before every timed step",
             "nodes_per_tile": info["nodes_per_tile"], "max_tile_span": info["max_tile_span"],
             "variant": info["variant"], "duplicate_fraction": round(info["duplicate_fraction"], 4),
+            "scan_operands": "16-bit fixed point (2 per LDS.32)" if bpg == 2 else "float32",
             "timing": "sum of per-step CUDA-event times on the launching stream, max over ranks",
         },
         "e2e": {"value": N_global * T / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": int(onsets_lin.nbytes),
@@ -384,10 +390,12 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
             "algorithmic_bytes_per_launch": b_alg,
             "note": "effective bandwidth per SURVEY 8(d): operands are served from shared memory after "
                     "one compulsory HBM pass, so frac may exceed 1; the binding pipe is shared memory",
-            "smem_pipe": {"achieved_gather_adds_per_s": ga, "peak_gather_adds_per_s": smem_peak,
-                          "frac": ga / smem_peak, "sm_mhz_used": sm_mhz,
-                          "measured_peak_gather_adds_per_s": measured_pipe,
-                          "frac_of_measured": ga / measured_pipe,
+            "smem_pipe": {"achieved_gather_adds_per_s": ga, "bytes_per_gather": bpg,
+                          "peak_gather_adds_per_s": smem_peak * 4 / bpg,
+                          "peak_gather_adds_per_s_fp32_operands": smem_peak,
+                          "frac": ga * bpg / (smem_peak * 4), "sm_mhz_used": sm_mhz,
+                          "measured_peak_gather_adds_per_s": measured_pipe * 4 / bpg,
+                          "frac_of_measured": ga * bpg / (measured_pipe * 4),
                           "measured_how": "qmb_microbench_smem_pipe: bare LDS.32+FADD streams, 12 warps/SM, same box, same run"},
         },
         "wall_s_timed_region": wall,

@@ -72,6 +72,8 @@ SIGNATURES = {
     "qmb_ctx_destroy": (ctypes.c_int, [c_void_p]),
     "qmb_ctx_sync": (ctypes.c_int, [c_void_p]),
     "qmb_ctx_set_variant": (ctypes.c_int, [c_void_p, ctypes.c_int]),
+    "qmb_ctx_set_scan_precision": (ctypes.c_int, [c_void_p, ctypes.c_int]),
+    "qmb_ctx_last_scan_bytes_per_gather": (ctypes.c_int, [c_void_p, ctypes.POINTER(ctypes.c_int)]),
     "qmb_ctx_launch_count": (ctypes.c_int, [c_void_p, ctypes.POINTER(c_int64)]),
     "qmb_ctx_flush_l2": (ctypes.c_int, [c_void_p]),
     "qmb_host_register": (ctypes.c_int, [c_void_p, c_int64]),

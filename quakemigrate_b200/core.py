@@ -213,7 +213,7 @@ class DeviceWaveforms:
 class Engine:
     """One GPU context: streams, scratch, optional NCCL communicator."""
 
-    def __init__(self, device: int = 0, variant: int | None = None):
+    def __init__(self, device: int = 0, variant: int | None = None, precision: str | None = None):
         self._lib = _lib.load()
         h = ctypes.c_void_p()
         _lib.check(self._lib.qmb_ctx_create(int(device), ctypes.byref(h)))
@@ -224,6 +224,8 @@ class Engine:
             # kernel tiling variant (consumer warps x nodes per warp x samples per lane), see
             # QMB_VARIANTS in csrc/qmb_internal.cuh; applies to tables uploaded afterwards
             _lib.check(self._lib.qmb_ctx_set_variant(self._h, int(variant)))
+        if precision is not None:
+            self.set_scan_precision(precision)
 
     # -- lifetime ---------------------------------------------------------------------------
     def __enter__(self):
@@ -246,6 +248,22 @@ class Engine:
 
     def sync(self):
         _lib.check(self._lib.qmb_ctx_sync(self._h))
+
+    def set_scan_precision(self, precision: str):
+        """
+        Operand format of the detect scan's gathers: ``"q16"`` (default; 16-bit fixed-point rows,
+        two samples per shared-memory word) or ``"fp32"``.  Results (arg-max indices, ``max_coa``)
+        are decided in float64 among the candidates inside the error band either way.
+        """
+        if precision not in ("q16", "fp32"):
+            raise ValueError("precision must be 'q16' or 'fp32'")
+        _lib.check(self._lib.qmb_ctx_set_scan_precision(self._h, 1 if precision == "fp32" else 0))
+
+    @property
+    def last_scan_bytes_per_gather(self) -> int:
+        n = ctypes.c_int(0)
+        _lib.check(self._lib.qmb_ctx_last_scan_bytes_per_gather(self._h, ctypes.byref(n)))
+        return n.value
 
     @property
     def launch_count(self) -> int:

@@ -53,6 +53,7 @@ extern "C" int qmb_ctx_create(int device, qmb_ctx_t *out) {
   ctx->sm_count = prop.multiProcessorCount;
   QMB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 4; ++i) QMB_CUDA(cudaEventCreate(&ctx->ev[i]));
+  if (const char *pr = getenv("QMB_SCAN_PRECISION")) ctx->scan_fp32 = strcmp(pr, "fp32") == 0 ? 1 : 0;
   const char *v = getenv("QMB_VARIANT");
   if (v && atoi(v) >= 0 && atoi(v) < QMB_N_VARIANTS) ctx->variant = atoi(v);
   *out = ctx;
@@ -64,6 +65,18 @@ extern "C" int qmb_ctx_set_variant(qmb_ctx_t ctx, int variant) {
   if (variant < 0) variant = QMB_DEFAULT_VARIANT;
   if (variant >= QMB_N_VARIANTS) QMB_FAIL(QMB_ERR_ARG, "variant must be in [0, %d)", QMB_N_VARIANTS);
   ctx->variant = variant;
+  return QMB_OK;
+}
+
+extern "C" int qmb_ctx_set_scan_precision(qmb_ctx_t ctx, int fp32) {
+  if (!ctx) QMB_FAIL(QMB_ERR_ARG, "null context");
+  ctx->scan_fp32 = fp32 ? 1 : 0;
+  return QMB_OK;
+}
+
+extern "C" int qmb_ctx_last_scan_bytes_per_gather(qmb_ctx_t ctx, int *bytes) {
+  if (!ctx || !bytes) QMB_FAIL(QMB_ERR_ARG, "null argument");
+  *bytes = ctx->last_scan_q16 ? 2 : 4;
   return QMB_OK;
 }
 
@@ -118,6 +131,7 @@ extern "C" int qmb_ctx_destroy(qmb_ctx_t ctx) {
   qmb_fft_release(ctx);
   if (ctx->tmp_onsets) {
     ctx->tmp_onsets->log32.release(); ctx->tmp_onsets->log64.release(); ctx->tmp_onsets->rowmax.release();
+    ctx->tmp_onsets->q16.release(); ctx->tmp_onsets->qrange.release();
     delete ctx->tmp_onsets;
     ctx->tmp_onsets = nullptr;
   }
@@ -353,7 +367,7 @@ extern "C" int qmb_lut_free(qmb_lut_t L) {
   if (!L) return QMB_OK;
   cudaSetDevice(L->device);
   L->tau16.release(); L->tmin.release(); L->span.release(); L->nodeidx.release();
-  L->boxes.release(); L->slotmap.release();
+  L->boxes.release(); L->slotmap.release(); L->tauq16.release();
   delete L;
   return QMB_OK;
 }
@@ -375,7 +389,7 @@ extern "C" int qmb_lut_info(qmb_lut_t L, qmb_lut_info_t *info) {
 extern "C" int qmb_onsets_free(qmb_onsets_t O) {
   if (!O) return QMB_OK;
   cudaSetDevice(O->device);
-  O->log32.release(); O->log64.release(); O->rowmax.release();
+  O->log32.release(); O->log64.release(); O->rowmax.release(); O->q16.release(); O->qrange.release();
   delete O;
   return QMB_OK;
 }

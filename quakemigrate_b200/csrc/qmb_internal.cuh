@@ -94,6 +94,8 @@ struct qmb_ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t launches = 0;
+  int scan_fp32 = 0;      // 1: detect scans gather float32 rows (default: 16-bit fixed point)
+  int last_scan_q16 = 0;  // what the last detect scan actually used
 
   // NCCL
   void *nccl_comm = nullptr;
@@ -146,6 +148,11 @@ struct qmb_lut {
   DevBuf<uint32_t> nodeidx; // [n_tiles][NB]         global flat node index or 0xFFFFFFFF (pad)
   DevBuf<int> boxes;        // [n_tiles][9]          tile origin, shape, region end
   DevBuf<uint32_t> slotmap; // [n_local]             tile * NB + slot of each local node
+  // 16-bit scan: word offset of (tile, row, slot) inside the staged row = (tau16 >> 1), plus
+  // RSq / 2 when tau16 is odd (the pair then comes from the "odd" stream staged behind the
+  // "even" one); RSq = elements per staged stream
+  DevBuf<uint16_t> tauq16;  // [n_tiles][Spad][NB]
+  int32_t RSq = 0;
 };
 
 struct qmb_ttgrids {  // every (station, phase) travel-time grid, float64 seconds, on the device
@@ -165,6 +172,15 @@ struct qmb_onsets {
   DevBuf<float> log32;    // [S][stride]
   DevBuf<double> log64;   // [S][stride]
   DevBuf<double> rowmax;  // [S] max |log onset| per row (for the fp32 error bound)
+  // 16-bit fixed-point copy for the detect scan: u = rint((x - qmin) / qstep) in [0, 65535].
+  // Two streams per row over a common position axis pos = qfront + sample:
+  //   stream 0 ("even"): q16[(2 s + 0) * qstride + pos] = u(sample)
+  //   stream 1 ("odd") : q16[(2 s + 1) * qstride + pos] = u(sample + 1)
+  // so that the pair (u(i), u(i + 1)) is one aligned 32-bit word for every i.
+  DevBuf<uint16_t> q16;
+  DevBuf<double> qrange;  // [S][2] min / max of each row
+  int64_t qstride = 0, qfront = 0;
+  double qmin = 0.0, qstep = 0.0;  // qstep == 0: no quantised copy (e.g. rows of the T1 migrate())
 };
 
 struct qmb_waveforms {  // device-resident float64 traces, (C, n) C-order
@@ -177,6 +193,7 @@ struct qmb_waveforms {  // device-resident float64 traces, (C, n) C-order
 
 constexpr int64_t QMB_ONSET_FRONT = 4;     // leading pad (elements); alignment slack
 constexpr int64_t QMB_ONSET_TAIL = 1024;   // trailing zero pad: >= time tile + max tile span + 8
+constexpr int64_t QMB_ONSET_QFRONT = 8;    // leading pad of the 16-bit streams (elements; 16 bytes)
 
 // ---------------------------------------------------------------------------------------------
 // cross-file entry points
@@ -187,8 +204,10 @@ struct QmbServeSource {  // float64 travel-time grids resident on the device (qm
   double sr;
   long long stride, node0;
 };
+int qmb_lut_rsq(const qmb_lut *L);
 int qmb_lut_build(qmb_ctx *ctx, qmb_lut *L, const int32_t *d_raw, const QmbServeSource *src = nullptr);
 int qmb_onsets_prepare(qmb_ctx *ctx, qmb_onsets *O, const double *d_linear /* (S,P) */, int already_log);
+int qmb_onsets_quantise(qmb_ctx *ctx, qmb_onsets *O);
 int qmb_scan_run(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, int32_t fsmp, int32_t lsmp,
                  int32_t available, float *kernel_ms);
 int qmb_window_run(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, int32_t fsmp, int32_t lsmp,

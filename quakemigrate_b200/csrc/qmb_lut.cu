@@ -4,11 +4,13 @@
 // axis fastest (quakemigrate/core/src/migratelib.c:53; produced by LUT.serve_traveltimes,
 // quakemigrate/lut/lut.py:502-538).  The scan kernel wants, per spatially compact TILE of nodes
 // (4x4x4 or 4x4x8) and per onset row:
-//     tmin4  = (min over the tile of max(0,tau)) rounded down to a multiple of 4 samples
-//     tau16  = max(0,tau) - tmin4   (uint16; the tile's tau-range is small because it is compact)
+//     tmin   = (min over the tile of max(0,tau)) rounded down to a multiple of 8 samples
+//     tau16  = max(0,tau) - tmin    (uint16; the tile's tau-range is small because it is compact)
 //     span   = max over the tile of tau16
-// so that one 16-byte-aligned bulk copy of  [tmin4, tmin4 + span + time_tile)  of the onset row
-// serves every node of the tile.  The clamp of negative travel times (migratelib.c:55) is
+// so that one 16-byte-aligned bulk copy of  [tmin, tmin + span + time_tile)  of the onset row
+// (float32: 4 samples per 16 bytes; 16-bit fixed point: 8) serves every node of the tile.
+//     tauq16 = word offset of the node's sample PAIR inside the staged 16-bit row (see
+//              qmb_internal.cuh): tau16 >> 1, plus RSq / 2 for odd tau16 ("odd" stream).  The clamp of negative travel times (migratelib.c:55) is
 // applied here, once.
 #include <stdlib.h>
 #include <string.h>
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(LT_THREADS) k_lut_tile(LutTileParams p) {
         mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
         mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
       }
-      const int base = mn & ~3;
+      const int base = mn & ~7;  // 16-byte aligned window starts for the float32 AND the 16-bit rows
       const int sp = mx - base;
       if (sp > 65535) overflow = 1;
       for (int q = lane; q < p.NB; q += 32) {
@@ -126,7 +128,21 @@ __global__ void __launch_bounds__(LT_THREADS) k_lut_tile(LutTileParams p) {
   }
 }
 
+__global__ void __launch_bounds__(256) k_lut_tauq(const uint16_t *tau16, uint16_t *tauq16, size_t n, int half_words) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned t = tau16[i];
+  tauq16[i] = (uint16_t)((t >> 1) + (t & 1u) * (unsigned)half_words);
+}
+
 }  // namespace
+
+// Elements per staged 16-bit stream for this table: the widest window [tmin, tmin + span + TT + 1]
+// rounded up to 16 bytes, plus 8 elements so that consecutive rows do not start on the same bank.
+int qmb_lut_rsq(const qmb_lut *L) {
+  const int TT = 32 * L->v.K;
+  return ((L->max_span + TT + 2 + 7) & ~7) + 8;
+}
 
 // ---------------------------------------------------------------------------------------------
 // host: cover the slab with node tiles.  The bulk uses the variant's preferred shape; what does
@@ -241,6 +257,18 @@ static int lut_build_variant(qmb_ctx *ctx, qmb_lut *L, const int32_t *d_raw, con
     QMB_FAIL(QMB_ERR_UNSUPPORTED,
              "travel-time range inside one %dx%dx%d node tile exceeds 65535 samples", L->tx, L->ty,
              L->tz);
+  // offsets for the 16-bit scan (needs max_span); skipped when they would not fit 16 bits
+  L->RSq = qmb_lut_rsq(L);
+  if ((L->v.K & 1) == 0 && L->max_span / 2 + L->RSq / 2 < 65536) {
+    const size_t n = (size_t)L->n_tiles * L->Spad * L->NB;
+    QMB_TRY(L->tauq16.ensure(n));
+    k_lut_tauq<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(L->tau16.p, L->tauq16.p, n, L->RSq / 2);
+    ctx->launches++;
+    QMB_CUDA(cudaGetLastError());
+  } else {
+    L->RSq = 0;
+    L->tauq16.release();
+  }
   return QMB_OK;
 }
 

@@ -15,6 +15,8 @@
 // where the reference's sliding sums keep the rounding residue of the transient forever).
 #include <math.h>
 
+#include <vector>
+
 #include "qmb_internal.cuh"
 
 namespace {
@@ -219,7 +221,90 @@ __global__ void __launch_bounds__(256) k_onset_prepare(PrepParams p) {
   }
 }
 
+// ---- 16-bit fixed-point rows for the detect scan -------------------------------------------------
+// range[2 s], range[2 s + 1] = min, max of the log-onset row s (valid samples only)
+__global__ void __launch_bounds__(256) k_onset_range(const double *log64, long long stride, long long front,
+                                                     long long P, double *range) {
+  const int s = blockIdx.x;
+  const double *row = log64 + (size_t)s * stride + front;
+  double mn = INFINITY, mx = -INFINITY;
+  for (long long i = threadIdx.x; i < P; i += blockDim.x) {
+    const double v = row[i];
+    mn = fmin(mn, v);
+    mx = fmax(mx, v);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  __shared__ double smn[8], smx[8];
+  if ((threadIdx.x & 31) == 0) {
+    smn[threadIdx.x >> 5] = mn;
+    smx[threadIdx.x >> 5] = mx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) {
+      mn = fmin(mn, smn[w]);
+      mx = fmax(mx, smx[w]);
+    }
+    range[2 * s] = mn;
+    range[2 * s + 1] = mx;
+  }
+}
+
+// u(i) = rint((x_i - qmin) / qstep) clamped to [0, 65535]; 0 outside the row.  Position pos holds
+// u(pos - qfront) in the even stream and u(pos - qfront + 1) in the odd stream.
+__global__ void __launch_bounds__(256) k_onset_quantise(const double *log64, long long stride, long long front,
+                                                        long long P, uint16_t *q16, long long qstride,
+                                                        long long qfront, double qmin, double inv_step) {
+  const int s = blockIdx.y;
+  const long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= qstride) return;
+  const double *row = log64 + (size_t)s * stride + front;
+  auto quant = [&](long long i) -> uint16_t {
+    if (i < 0 || i >= P) return (uint16_t)0;
+    const double u = rint((row[i] - qmin) * inv_step);
+    return (uint16_t)fmin(fmax(u, 0.0), 65535.0);
+  };
+  const long long i = pos - qfront;
+  q16[((size_t)2 * s + 0) * qstride + pos] = quant(i);
+  q16[((size_t)2 * s + 1) * qstride + pos] = quant(i + 1);
+}
+
 }  // namespace
+
+// Build the 16-bit streams of O (after its float64 rows exist).  One common grid for all rows:
+// qmin = the smallest value present (so that the clip floor, the most frequent value of real
+// onsets, is represented exactly), qstep = (max - min) / 65535.
+int qmb_onsets_quantise(qmb_ctx *ctx, qmb_onsets *O) {
+  O->qstep = 0.0;
+  if (O->S <= 0 || O->P <= 0) return QMB_OK;
+  QMB_TRY(O->qrange.ensure((size_t)2 * O->S));
+  k_onset_range<<<O->S, 256, 0, ctx->stream>>>(O->log64.p, O->stride, O->front, O->P, O->qrange.p);
+  ctx->launches++;
+  QMB_CUDA(cudaGetLastError());
+  std::vector<double> range((size_t)2 * O->S);
+  QMB_CUDA(cudaMemcpyAsync(range.data(), O->qrange.p, range.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  QMB_CUDA(cudaStreamSynchronize(ctx->stream));
+  double mn = range[0], mx = range[1];
+  for (int s = 0; s < O->S; ++s) {
+    if (range[2 * s] < mn) mn = range[2 * s];
+    if (range[2 * s + 1] > mx) mx = range[2 * s + 1];
+  }
+  if (!(mn <= mx) || !isfinite(mn) || !isfinite(mx)) return QMB_OK;  // NaN/inf rows: float32 scan only
+  O->qmin = mn;
+  O->qstep = mx > mn ? (mx - mn) / 65535.0 : 1.0;
+  O->qfront = QMB_ONSET_QFRONT;
+  O->qstride = ((O->qfront + O->P + QMB_ONSET_TAIL + 7) / 8) * 8;
+  QMB_TRY(O->q16.ensure((size_t)2 * O->S * O->qstride));
+  dim3 grid((unsigned)((O->qstride + 255) / 256), (unsigned)O->S);
+  k_onset_quantise<<<grid, 256, 0, ctx->stream>>>(O->log64.p, O->stride, O->front, O->P, O->q16.p, O->qstride,
+                                                  O->qfront, O->qmin, 1.0 / O->qstep);
+  ctx->launches++;
+  QMB_CUDA(cudaGetLastError());
+  return QMB_OK;
+}
 
 int qmb_stalta_device(qmb_ctx *ctx, const double *d_signal, int32_t n_channels, int64_t n,
                       int64_t stride, int32_t nsta, int32_t nlta, int32_t position,
@@ -290,7 +375,11 @@ int qmb_onsets_prepare(qmb_ctx *ctx, qmb_onsets *O, const double *d_linear, int 
   k_onset_prepare<<<grid, 256, 0, ctx->stream>>>(p);
   ctx->launches++;
   QMB_CUDA(cudaGetLastError());
-  return QMB_OK;
+  if (already_log) {  // rows of the reference-compatible migrate(): float32 window pass only
+    O->qstep = 0.0;
+    return QMB_OK;
+  }
+  return qmb_onsets_quantise(ctx, O);
 }
 
 int qmb_onsets_combine(qmb_ctx *ctx, qmb_onsets *O, const double *d_chan, int64_t chan_stride,
@@ -306,5 +395,5 @@ int qmb_onsets_combine(qmb_ctx *ctx, qmb_onsets *O, const double *d_chan, int64_
   k_onset_prepare<<<grid, 256, 0, ctx->stream>>>(p);
   ctx->launches++;
   QMB_CUDA(cudaGetLastError());
-  return QMB_OK;
+  return qmb_onsets_quantise(ctx, O);
 }

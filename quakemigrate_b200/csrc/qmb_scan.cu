@@ -19,6 +19,10 @@
 //               each lane keeps, for its K samples, the running top-3 values (with the node
 //               indices of the top two) and the float64 sum of exp(stack / available).
 //
+// MODE 4 (default for detect): the rows are staged as 16-bit fixed point, two samples per 32-bit
+// word, so one LDS.32 feeds two gather-adds and the stacks are exact integer sums of the quantised
+// rows; delta below becomes S * qstep / 2 (+ float32 conversion).  MODE 0 / 1 keep float32 rows.
+//
 // Exactness of the arg-max.  Stacks are accumulated in float32 in station order.  With
 //   delta = n_rows * 2^-24 * sum_rows max|log onset|   (rigorous bound on |fp32 stack - exact|)
 // a node whose fp32 stack is more than 2*delta below the fp32 maximum cannot be the float64
@@ -93,6 +97,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
 struct ScanParams {
   // onsets
   const float *on32;     // [S][row_stride]
+  // MODE 4 (16-bit fixed point): [S][2][row_stride] uint16, see qmb_onsets in qmb_internal.cuh;
+  // stack = qc0 + qstep * sum(u)
+  const uint16_t *on16;
+  float qstep, qc0;
   long long row_stride;  // elements
   long long t_origin;    // index within a row of (tau = 0, sample t' = 0); multiple of 4
   int S, n_chunks;       // n_chunks = stages per node tile (rows / CR)
@@ -164,10 +172,12 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
           int tmin = 0, len = 0;
           if (act) {
             tmin = p.tmin[(size_t)j * p.Spad + s];
-            len = ((int)p.span[(size_t)j * p.Spad + s] + TT + 3) & ~3;
+            if constexpr (MODE == 4) len = ((int)p.span[(size_t)j * p.Spad + s] + TT + 2 + 7) & ~7;
+            else len = ((int)p.span[(size_t)j * p.Spad + s] + TT + 3) & ~3;
           }
-          uint32_t bytes = (uint32_t)len * 4u;
-          uint32_t total = bytes;
+          // MODE 4: `bytes` per stream (2 bytes per sample), two streams per row
+          uint32_t bytes = MODE == 4 ? (uint32_t)len * 2u : (uint32_t)len * 4u;
+          uint32_t total = MODE == 4 ? 2u * bytes : bytes;
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
           total += tau_bytes + (c == 0 ? (uint32_t)NB * 4u : 0u);
@@ -176,9 +186,17 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
           const uint32_t stage = smem_base + (uint32_t)st * p.stage_bytes;
           if (lane == 0) mbar_expect_tx(full, total);
           __syncwarp();
-          if (act)
+          if constexpr (MODE == 4) {
+            if (act) {
+              const uint16_t *src = p.on16 + (size_t)2 * s * p.row_stride + tbase + tmin;
+              const uint32_t dst = stage + (uint32_t)lane * p.RS * 4u;
+              bulk_g2s(dst, src, bytes, full);                                       // pairs (2i, 2i+1)
+              bulk_g2s(dst + (uint32_t)p.RS * 2u, src + p.row_stride, bytes, full);  // pairs (2i+1, 2i+2)
+            }
+          } else if (act) {
             bulk_g2s(stage + (uint32_t)lane * p.RS * 4u, p.on32 + (size_t)s * p.row_stride + tbase + tmin,
                      bytes, full);
+          }
           if (lane == 0)
             bulk_g2s(stage + rows_bytes, p.tau16 + ((size_t)j * p.Spad + (size_t)c * CR) * NB,
                      tau_bytes, full);
@@ -206,6 +224,122 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
       m1[k] = m2[k] = m3[k] = NEG_INF;
       i1[k] = i2[k] = 0xFFFFFFFFu;
       sum[k] = 0.0;
+    }
+
+    if constexpr (MODE == 4) {
+      // ---- 16-bit fixed-point rows: lane l owns the sample PAIRS (64 kk + 2 l, + 1), kk < K/2.
+      // One LDS.32 fetches both samples of a pair (half the shared-memory bytes per gather-add);
+      // A accumulates the whole words, Hs their upper halves: sum(lo) = A - (Hs << 16) exactly
+      // (mod 2^32, and sum(lo) < 2^32), sum(hi) = Hs.
+      static_assert(NPW == 4 && (K % 2) == 0, "16-bit scan is built for 4 nodes per warp");
+      constexpr int KW = K / 2, H = NPW / 2;
+      for (int j = tile0; j < tile1; ++j) {
+        uint32_t A[NPW][KW], Hs[NPW][KW];
+#pragma unroll
+        for (int q = 0; q < NPW; ++q)
+#pragma unroll
+          for (int k = 0; k < KW; ++k) A[q][k] = Hs[q][k] = 0u;
+        uint32_t nidx[NPW];
+        for (int c = 0; c < p.n_chunks; ++c) {
+          const uint32_t full = bar_base + 8u * st, empty = bar_base + 8u * (p.n_stages + st);
+          const uint32_t stage = smem_base + (uint32_t)st * p.stage_bytes;
+          mbar_wait(full, ph);
+          if (c == 0) {
+            const uint32_t ia = stage + rows_bytes + tau_bytes + (uint32_t)(warp * NPW) * 4u;
+#pragma unroll
+            for (int q = 0; q < NPW; ++q)
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(nidx[q]) : "r"(ia + 4u * q));
+          }
+          const int nrows = min(CR, p.S - c * CR);
+          const uint32_t tau_addr = stage + rows_bytes + (uint32_t)(warp * NPW) * 2u;
+          uint32_t row_addr = stage + (uint32_t)lane * 4u;
+          auto load_off = [&](int sl, uint32_t (&off)[NPW]) {
+            uint32_t a, b;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(tau_addr + (uint32_t)sl * NB * 2u));
+            off[0] = a & 0xffffu; off[1] = a >> 16; off[2] = b & 0xffffu; off[3] = b >> 16;
+          };
+          auto load_half = [&](int h, const uint32_t (&off)[NPW], uint32_t base, uint32_t (&v)[H][KW]) {
+#pragma unroll
+            for (int q = 0; q < H; ++q) {
+              const uint32_t a = base + off[h * H + q] * 4u;
+#pragma unroll
+              for (int k = 0; k < KW; ++k)
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v[q][k]) : "r"(a + 128u * k));
+            }
+          };
+          auto add_half = [&](int h, const uint32_t (&v)[H][KW]) {
+#pragma unroll
+            for (int q = 0; q < H; ++q)
+#pragma unroll
+              for (int k = 0; k < KW; ++k) {
+                A[h * H + q][k] += v[q][k];
+                Hs[h * H + q][k] += v[q][k] >> 16;
+              }
+          };
+          uint32_t off[NPW], off_next[NPW];
+          uint32_t v0[H][KW], v1[H][KW];
+          load_off(0, off);
+          load_half(0, off, row_addr, v0);
+#pragma unroll 2
+          for (int sl = 0; sl + 1 < nrows; ++sl) {
+            load_half(1, off, row_addr, v1);
+            load_off(sl + 1, off_next);
+            add_half(0, v0);
+            row_addr += (uint32_t)p.RS * 4u;
+            load_half(0, off_next, row_addr, v0);
+            add_half(1, v1);
+#pragma unroll
+            for (int q = 0; q < NPW; ++q) off[q] = off_next[q];
+          }
+          load_half(1, off, row_addr, v1);
+          add_half(0, v0);
+          add_half(1, v1);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty);
+          if (++st == p.n_stages) { st = 0; ph ^= 1u; }
+        }
+        // ---- per-tile epilogue: slot k = 2 kk + h <-> sample 64 kk + 2 lane + h ---------------
+#pragma unroll
+        for (int kk = 0; kk < KW; ++kk) {
+          float e0 = 0.f, e1 = 0.f;
+#pragma unroll
+          for (int q = 0; q < NPW; ++q) {
+            const bool pad = nidx[q] == 0xFFFFFFFFu;
+            const uint32_t hi = Hs[q][kk], lo = A[q][kk] - (hi << 16);
+            const float vv[2] = {pad ? NEG_INF : fmaf((float)lo, p.qstep, p.qc0),
+                                 pad ? NEG_INF : fmaf((float)hi, p.qstep, p.qc0)};
+            e0 += ex2_approx(vv[0] * p.scale);
+            e1 += ex2_approx(vv[1] * p.scale);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int k = 2 * kk + h;
+              const float v = vv[h];
+              const bool g1 = v > m1[k];
+              const bool g2 = v > m2[k];
+              m3[k] = g2 ? m2[k] : fmaxf(m3[k], v);
+              m2[k] = g1 ? m1[k] : (g2 ? v : m2[k]);
+              i2[k] = g1 ? i1[k] : (g2 ? nidx[q] : i2[k]);
+              m1[k] = g1 ? v : m1[k];
+              i1[k] = g1 ? nidx[q] : i1[k];
+            }
+          }
+          sum[2 * kk] += (double)e0;
+          sum[2 * kk + 1] += (double)e1;
+        }
+      }
+      // ---- item done: publish (pairs of neighbouring samples -> 8 / 16-byte stores) -----------
+      const size_t base = ((size_t)r * W + warp) * p.Tpad + (size_t)tt * TT + 2u * lane;
+#pragma unroll
+      for (int kk = 0; kk < KW; ++kk) {
+        const size_t o = base + 64u * kk;
+        *reinterpret_cast<float2 *>(p.pm1 + o) = make_float2(m1[2 * kk], m1[2 * kk + 1]);
+        *reinterpret_cast<float2 *>(p.pm2 + o) = make_float2(m2[2 * kk], m2[2 * kk + 1]);
+        *reinterpret_cast<float2 *>(p.pm3 + o) = make_float2(m3[2 * kk], m3[2 * kk + 1]);
+        *reinterpret_cast<uint2 *>(p.pi1 + o) = make_uint2(i1[2 * kk], i1[2 * kk + 1]);
+        *reinterpret_cast<uint2 *>(p.pi2 + o) = make_uint2(i2[2 * kk], i2[2 * kk + 1]);
+        *reinterpret_cast<double2 *>(p.psum + o) = make_double2(sum[2 * kk], sum[2 * kk + 1]);
+      }
+      continue;
     }
 
     for (int j = tile0; j < tile1; ++j) {
@@ -597,6 +731,17 @@ int dispatch_scan(qmb_ctx *ctx, const QmbVariant &v, const ScanParams &p, int gr
   QMB_FAIL(QMB_ERR_ARG, "unknown kernel variant %d", v.id);
 }
 
+// 16-bit fixed-point detect scan: built for the 4-nodes-per-warp variants
+bool q16_variant(const QmbVariant &v) { return v.id == 4 || v.id == 6 || v.id == 7; }
+int dispatch_scan_q16(qmb_ctx *ctx, const QmbVariant &v, const ScanParams &p, int grid, size_t smem) {
+  switch (v.id) {
+    case 4: return launch_scan<12, 4, 8, 4, 16>(ctx, p, grid, smem);
+    case 6: return launch_scan<8, 4, 8, 4, 16>(ctx, p, grid, smem);
+    case 7: return launch_scan<12, 4, 8, 4, 32>(ctx, p, grid, smem);
+  }
+  QMB_FAIL(QMB_ERR_ARG, "kernel variant %d has no 16-bit form", v.id);
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -604,20 +749,33 @@ int dispatch_scan(qmb_ctx *ctx, const QmbVariant &v, const ScanParams &p, int gr
 // ---------------------------------------------------------------------------------------------
 // Tiling decisions shared by the detect scan and the window pass.
 static int scan_setup(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, long long first, long long T,
-                      int32_t available, ScanParams &p, size_t &smem, int &shift_out) {
+                      int32_t available, ScanParams &p, size_t &smem, int &shift_out, bool use_q = false) {
   const int K = L->v.K, TT = 32 * K, NB = L->NB;
   p.on32 = O->log32.p;
   p.row_stride = O->stride;
-  const int shift = (int)((O->front + first) & 3);  // time tiles start `shift` samples early
+  long long front = O->front;
+  int align = 3;  // time tiles start on 16-byte boundaries of the staged rows
+  p.tau16 = L->tau16.p;
+  p.RS = ((L->max_span + TT + 3) & ~3) + 4;
+  if (use_q) {  // 16-bit fixed-point rows (detect scan only)
+    p.on16 = O->q16.p;
+    p.row_stride = O->qstride;
+    front = O->qfront;
+    align = 7;
+    p.tau16 = L->tauq16.p;
+    p.RS = L->RSq;  // elements per stream; a staged row is two streams = RS * 4 bytes, as for float32
+    p.qstep = (float)O->qstep;
+    p.qc0 = (float)((double)L->S * O->qmin);
+  }
+  const int shift = (int)((front + first) & align);  // time tiles start `shift` samples early
   shift_out = shift;
   p.shift = shift;
   p.T = T;
-  p.t_origin = O->front + first - shift;
+  p.t_origin = front + first - shift;
   p.S = L->S;
   p.n_chunks = L->Spad / L->chunk_rows;
-  p.tau16 = L->tau16.p; p.tmin = L->tmin.p; p.span = L->span.p; p.nodeidx = L->nodeidx.p;
+  p.tmin = L->tmin.p; p.span = L->span.p; p.nodeidx = L->nodeidx.p;
   p.n_tiles = L->n_tiles; p.Spad = L->Spad;
-  p.RS = ((L->max_span + TT + 3) & ~3) + 4;
   p.stage_bytes = L->chunk_rows * p.RS * 4 + L->chunk_rows * NB * 2 + NB * 4;
   p.stage_bytes = (p.stage_bytes + 127) & ~127;
   const int avail_smem = QMB_SMEM_BUDGET - 1024;
@@ -700,7 +858,11 @@ int qmb_scan_run(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, int32_t fsmp, int32_t 
   ScanParams p = {};
   size_t smem;
   int shift;
-  QMB_TRY(scan_setup(ctx, L, O, fsmp, T, available, p, smem, shift));
+  // detect scans read 16-bit fixed-point rows unless float32 was asked for (or the table / rows
+  // have no 16-bit form); candidates are re-evaluated in float64 either way
+  const bool use_q = !ctx->scan_fp32 && O->qstep > 0.0 && O->q16.p && L->RSq > 0 && L->tauq16.p &&
+                     q16_variant(L->v) && O->S <= 256;  // sum(u) < 2^24: exact in float32
+  QMB_TRY(scan_setup(ctx, L, O, fsmp, T, available, p, smem, shift, use_q));
   const int R = p.R, grid = ctx->sm_count;
 
   const size_t n_part = (size_t)R * L->v.W * p.Tpad;
@@ -722,11 +884,20 @@ int qmb_scan_run(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, int32_t fsmp, int32_t 
   QMB_CUDA(cudaStreamSynchronize(ctx->stream));
   double A = 0.0;
   for (double v : rowmax) A += v;
-  const float thr = (float)(2.0 * 1.001 * (double)O->S * 5.9604644775390625e-08 * A) + 1e-30f;
+  float thr = (float)(2.0 * 1.001 * (double)O->S * 5.9604644775390625e-08 * A) + 1e-30f;
+  if (use_q) {
+    // |quantised stack - exact| <= S * qstep / 2 (rounding to the grid) + the float32 evaluation of
+    // qc0 + qstep * sum(u): rounding of qstep, of qc0 and of the fma, each <= 2^-24 of
+    // S * (|qmin| + 65535 qstep)
+    const double S = (double)O->S, mag = S * (fabs(O->qmin) + 65535.0 * O->qstep);
+    const double delta = 0.5 * S * O->qstep + 4.0 * 5.9604644775390625e-08 * mag;
+    thr = (float)(2.0 * 1.001 * delta) + 1e-30f;
+  }
+  ctx->last_scan_q16 = use_q ? 1 : 0;
 
   QMB_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
   int rc;
-  rc = dispatch_scan<0>(ctx, L->v, p, grid, smem);
+  rc = use_q ? dispatch_scan_q16(ctx, L->v, p, grid, smem) : dispatch_scan<0>(ctx, L->v, p, grid, smem);
   QMB_TRY(rc);
   QMB_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
 
