@@ -101,6 +101,11 @@ struct ScanParams {
   // stack = qc0 + qstep * sum(u)
   const uint16_t *on16;
   float qstep, qc0;
+  // 1 and 65536 as kernel parameters: multiplying by them keeps the word / upper-half accumulation
+  // on the fma pipe (IMAD, IMAD.HI) -- the compiler cannot fold a multiplier it does not know --
+  // while shifts and adds would all land on the alu pipe, which is the one that saturates
+  uint32_t q_one, q_64k;
+  int q_form;  // 0: IADD3 + LEA.HI (alu)   1: IMAD word sums   2: IMAD word sums + IMAD.HI for odd words
   long long row_stride;  // elements
   long long t_origin;    // index within a row of (tau = 0, sample t' = 0); multiple of 4
   int S, n_chunks;       // n_chunks = stages per node tile (rows / CR)
@@ -172,12 +177,12 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
           int tmin = 0, len = 0;
           if (act) {
             tmin = p.tmin[(size_t)j * p.Spad + s];
-            if constexpr (MODE == 4) len = ((int)p.span[(size_t)j * p.Spad + s] + TT + 2 + 7) & ~7;
+            if constexpr (MODE >= 4) len = ((int)p.span[(size_t)j * p.Spad + s] + TT + 2 + 7) & ~7;
             else len = ((int)p.span[(size_t)j * p.Spad + s] + TT + 3) & ~3;
           }
           // MODE 4: `bytes` per stream (2 bytes per sample), two streams per row
-          uint32_t bytes = MODE == 4 ? (uint32_t)len * 2u : (uint32_t)len * 4u;
-          uint32_t total = MODE == 4 ? 2u * bytes : bytes;
+          uint32_t bytes = MODE >= 4 ? (uint32_t)len * 2u : (uint32_t)len * 4u;
+          uint32_t total = MODE >= 4 ? 2u * bytes : bytes;
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
           total += tau_bytes + (c == 0 ? (uint32_t)NB * 4u : 0u);
@@ -186,7 +191,7 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
           const uint32_t stage = smem_base + (uint32_t)st * p.stage_bytes;
           if (lane == 0) mbar_expect_tx(full, total);
           __syncwarp();
-          if constexpr (MODE == 4) {
+          if constexpr (MODE >= 4) {
             if (act) {
               const uint16_t *src = p.on16 + (size_t)2 * s * p.row_stride + tbase + tmin;
               const uint32_t dst = stage + (uint32_t)lane * p.RS * 4u;
@@ -226,7 +231,8 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
       sum[k] = 0.0;
     }
 
-    if constexpr (MODE == 4) {
+    if constexpr (MODE >= 4) {
+      constexpr int QF = MODE - 4;
       // ---- 16-bit fixed-point rows: lane l owns the sample PAIRS (64 kk + 2 l, + 1), kk < K/2.
       // One LDS.32 fetches both samples of a pair (half the shared-memory bytes per gather-add);
       // A accumulates the whole words, Hs their upper halves: sum(lo) = A - (Hs << 16) exactly
@@ -272,8 +278,10 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
             for (int q = 0; q < H; ++q)
 #pragma unroll
               for (int k = 0; k < KW; ++k) {
-                A[h * H + q][k] += v[q][k];
-                Hs[h * H + q][k] += v[q][k] >> 16;
+                if constexpr (QF == 0) A[h * H + q][k] += v[q][k];
+                else A[h * H + q][k] = v[q][k] * p.q_one + A[h * H + q][k];
+                if (QF == 2 && (k & 1)) Hs[h * H + q][k] = __umulhi(v[q][k], p.q_64k) + Hs[h * H + q][k];
+                else Hs[h * H + q][k] += v[q][k] >> 16;
               }
           };
           uint32_t off[NPW], off_next[NPW];
@@ -731,13 +739,17 @@ int dispatch_scan(qmb_ctx *ctx, const QmbVariant &v, const ScanParams &p, int gr
   QMB_FAIL(QMB_ERR_ARG, "unknown kernel variant %d", v.id);
 }
 
+constexpr int QMB_Q16_FORM = 1;  // default accumulation form (see ScanParams::q_form)
 // 16-bit fixed-point detect scan: built for the 4-nodes-per-warp variants
 bool q16_variant(const QmbVariant &v) { return v.id == 4 || v.id == 6 || v.id == 7; }
 int dispatch_scan_q16(qmb_ctx *ctx, const QmbVariant &v, const ScanParams &p, int grid, size_t smem) {
   switch (v.id) {
-    case 4: return launch_scan<12, 4, 8, 4, 16>(ctx, p, grid, smem);
-    case 6: return launch_scan<8, 4, 8, 4, 16>(ctx, p, grid, smem);
-    case 7: return launch_scan<12, 4, 8, 4, 32>(ctx, p, grid, smem);
+    case 4: return launch_scan<12, 4, 8, 4 + QMB_Q16_FORM, 16>(ctx, p, grid, smem);
+    case 6: return launch_scan<8, 4, 8, 4 + QMB_Q16_FORM, 16>(ctx, p, grid, smem);
+    case 7:
+      if (p.q_form == 0) return launch_scan<12, 4, 8, 4, 32>(ctx, p, grid, smem);
+      if (p.q_form == 1) return launch_scan<12, 4, 8, 5, 32>(ctx, p, grid, smem);
+      return launch_scan<12, 4, 8, 6, 32>(ctx, p, grid, smem);
   }
   QMB_FAIL(QMB_ERR_ARG, "kernel variant %d has no 16-bit form", v.id);
 }
@@ -766,6 +778,10 @@ static int scan_setup(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, long long first, 
     p.RS = L->RSq;  // elements per stream; a staged row is two streams = RS * 4 bytes, as for float32
     p.qstep = (float)O->qstep;
     p.qc0 = (float)((double)L->S * O->qmin);
+    p.q_one = 1u;
+    p.q_64k = 65536u;
+    p.q_form = QMB_Q16_FORM;
+    if (const char *f = getenv("QMB_Q16_FORM")) p.q_form = atoi(f);
   }
   const int shift = (int)((front + first) & align);  // time tiles start `shift` samples early
   shift_out = shift;

@@ -12,6 +12,14 @@ print("$prec value %.4g ms/step %.2f scan_ms %.2f e2e %.4g slow %s pipe %s" % (j
 PY
   tail -3 gpurun_out/bench_n1_$prec.err
 done
+for form in 0 1 2; do
+  QMB_Q16_FORM=$form timeout 200 python bench.py --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/bench_form$form.json 2> gpurun_out/bench_form$form.err
+  python - <<PY
+import json
+j = json.load(open("gpurun_out/bench_form$form.json"))
+print("q16 form $form: value %.4g scan_ms %.2f slow %s" % (j["value"], j["roofline"]["kernel_ms"], j["slow_path_samples"]))
+PY
+done
 for extra in "$@"; do
   case $extra in
     ncu) timeout 200 ncu --set full --clock-control none --import-source on -k regex:k_scan -s 3 -c 1 -o gpurun_out/prof_scan_q16 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_d.log 2>&1

@@ -49,7 +49,7 @@ def test_oracle_spot_windows(full):
                                           threads=O.default_threads())
         assert np.array_equal(ix[a:a + 200], w_ix), f"window at {a}"
         np.testing.assert_allclose(mx[a:a + 200], w_mx, rtol=1e-9)
-        np.testing.assert_allclose(nm[a:a + 200], w_nm, rtol=2e-6)
+        np.testing.assert_allclose(nm[a:a + 200], w_nm, rtol=1e-5)
 
 
 def test_planted_events_recovered(full):

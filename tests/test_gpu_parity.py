@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 RTOL_COA = 1e-5          # stated tolerance of the north star
 RTOL_COA_TIGHT = 1e-9    # max_coa is re-evaluated in float64: expect ~1e-15
-RTOL_NORM = 2e-6         # normalised max uses the fp32 node-sum
+RTOL_NORM = 1e-5         # north_star bar; the node sum is built from 16-bit fixed-point (or fp32) stacks: 3e-6 observed on tiny grids, ~1e-7 at bench sizes
 
 
 def _oracle_kind():

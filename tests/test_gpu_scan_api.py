@@ -82,7 +82,7 @@ def test_compute_detect_and_locate(position):
     assert list(onset_data.availability.items()) == list(r_avail.items())
     assert np.array_equal(np.argmax(r_map4d.reshape(-1, r_map4d.shape[-1]), axis=0), r_idx)
     np.testing.assert_allclose(max_coa, r_max, rtol=1e-8)
-    np.testing.assert_allclose(max_coa_n, r_norm, rtol=2e-6)
+    np.testing.assert_allclose(max_coa_n, r_norm, rtol=1e-5)
     np.testing.assert_allclose(coord, r_coord, rtol=0, atol=0)      # identical arg-max -> identical coords
 
     # reference-shaped locate: the whole volume
