@@ -54,8 +54,8 @@ def parse_args():
     ap.add_argument("--workload", default="cfg2", choices=sorted(syn.CONFIGS))
     ap.add_argument("--variant", type=int, default=-1, help="kernel tiling variant id; -1 = library default")
     ap.add_argument("--samples", type=int, default=0, help="override n_samples (debug)")
-    ap.add_argument("--precision", default=None, choices=["q16", "fp32"],
-                    help="operand format of the scan's gathers (library default: q16)")
+    ap.add_argument("--precision", default=None, choices=["auto", "q16", "fp32"],
+                    help="operand format of the scan's gathers (library default: auto -> q16 at bench sizes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pre-only", action="store_true",
                     help="profiling aid: run only the pre-processing stage on the workload's full-length traces")
@@ -135,7 +135,7 @@ class ClockSampler:
 # CPU side: the reference's own C path (oracle/_ref) or, where it was not built, the oracle port
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_sample(cfg: syn.SynthConfig, prob: syn.SynthProblem, onsets_lin: np.ndarray,
-                         t_sub: int, warm: int, reps: int):
+                         t_sub: int, warm: int, reps: int, return_result: bool = False):
     """
     Time migrate + find_max_coa of the reference on a bounded sample: the full grid, the first
     `t_sub` output samples.  Returns (node-samples/s, kind, cores, seconds per rep).
@@ -150,13 +150,14 @@ def cpu_reference_sample(cfg: syn.SynthConfig, prob: syn.SynthProblem, onsets_li
     for i in range(warm + reps):
         t0 = time.perf_counter()
         m4 = O.migrate(sub, prob.traveltimes, prob.fsmp, prob.lsmp, cfg.n_rows, threads=cores, kind=kind)
-        O.find_max_coa(m4, threads=cores, kind=kind)
+        result = O.find_max_coa(m4, threads=cores, kind=kind)
         dt = time.perf_counter() - t0
         del m4
         if i >= warm:
             times.append(dt)
     sec = float(np.median(times))
-    return cfg.n_nodes * t_sub / sec, ("reference" if kind == "ref" else "port"), cores, sec
+    out = (cfg.n_nodes * t_sub / sec, ("reference" if kind == "ref" else "port"), cores, sec)
+    return out + (result,) if return_result else out
 
 
 def host_onsets(prob: syn.SynthProblem, position: str) -> np.ndarray:
@@ -405,7 +406,13 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
     if rank == 0 and world == 1:
         line["stages"] = {"preprocess": preprocess_stage(eng, cfg, prob, args, peak, peak_src)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, kind, cores, sec = cpu_reference_sample(cfg, prob, onsets_lin, 600, 1, 2)
+        v, kind, cores, sec, ref = cpu_reference_sample(cfg, prob, onsets_lin, 600, 1, 2, return_result=True)
+        n_cmp = len(ref[0])
+        line["parity_vs_reference_sample"] = {
+            "samples": n_cmp, "argmax_equal": bool(np.array_equal(res[2][:n_cmp], ref[2])),
+            "max_coa_max_rel": float(np.max(np.abs(res[0][:n_cmp] - ref[0]) / ref[0])),
+            "max_norm_coa_max_rel": float(np.max(np.abs(res[1][:n_cmp] - ref[1]) / ref[1])),
+            "note": "e2e result of this run against the reference C on the CPU-baseline sample"}
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                                 "sample": f"full {cfg.grid[0]}x{cfg.grid[1]}x{cfg.grid[2]} grid x first 600 of {T} "
                                           f"samples, migrate+find_max_coa, median of 2 after 1 warm-up ({sec:.2f} s each)"}

@@ -93,14 +93,16 @@ int qmb_ctx_destroy(qmb_ctx_t ctx);
 int qmb_ctx_sync(qmb_ctx_t ctx);
 /* kernel variant: nodes per warp (4 or 8); 0 = default.  Must be set before qmb_lut_upload. */
 int qmb_ctx_set_variant(qmb_ctx_t ctx, int nodes_per_warp);
-/* Operand format of the DETECT scan's gathers.  Default (fp32 == 0): onset rows staged as 16-bit
- * fixed point (two samples per 32-bit shared-memory word, exact integer stacks of the quantised
- * rows); fp32 != 0: float32 rows.  Either way the per-sample winner is decided among the
- * candidates inside a rigorous error band by re-evaluating them in float64 in the reference's
- * summation order, so the arg-max indices and max_coa do not depend on this choice.  Also settable
- * with QMB_SCAN_PRECISION=fp32.  qmb_ctx_last_scan_bytes_per_gather reports what the last detect
- * scan moved per gathered operand (2 or 4 bytes). */
-int qmb_ctx_set_scan_precision(qmb_ctx_t ctx, int fp32);
+/* Operand format of the DETECT scan's gathers: mode 0 = automatic (default), 1 = float32 rows,
+ * 2 = 16-bit fixed-point rows (two samples per 32-bit shared-memory word, exact integer stacks of
+ * the quantised rows).  Whatever the format, the per-sample winner is decided among the candidates
+ * inside a rigorous error band by re-evaluating them in float64 in the reference's summation
+ * order, so arg-max indices and max_coa do not depend on it; max_norm_coa divides by a node sum
+ * built from the scan's stacks, and the automatic mode keeps float32 rows whenever the estimated
+ * error of that sum is not clearly inside 1e-5 (tiny grids, `available` << rows).  Also settable
+ * with QMB_SCAN_PRECISION=fp32|q16.  qmb_ctx_last_scan_bytes_per_gather reports what the last
+ * detect scan moved per gathered operand (2 or 4 bytes). */
+int qmb_ctx_set_scan_precision(qmb_ctx_t ctx, int mode);
 int qmb_ctx_last_scan_bytes_per_gather(qmb_ctx_t ctx, int *bytes);
 /* number of launches of this library's own kernels since context creation */
 int qmb_ctx_launch_count(qmb_ctx_t ctx, int64_t *count);

@@ -251,13 +251,16 @@ class Engine:
 
     def set_scan_precision(self, precision: str):
         """
-        Operand format of the detect scan's gathers: ``"q16"`` (default; 16-bit fixed-point rows,
-        two samples per shared-memory word) or ``"fp32"``.  Results (arg-max indices, ``max_coa``)
-        are decided in float64 among the candidates inside the error band either way.
+        Operand format of the detect scan's gathers: ``"auto"`` (default: 16-bit fixed-point rows,
+        two samples per shared-memory word, whenever ``max_norm_coa`` stays clearly inside the
+        1e-5 bar; float32 rows on tiny grids), ``"q16"`` or ``"fp32"`` to force one.  Arg-max
+        indices and ``max_coa`` are decided in float64 among the candidates inside the error band
+        either way.
         """
-        if precision not in ("q16", "fp32"):
-            raise ValueError("precision must be 'q16' or 'fp32'")
-        _lib.check(self._lib.qmb_ctx_set_scan_precision(self._h, 1 if precision == "fp32" else 0))
+        modes = {"auto": 0, "fp32": 1, "q16": 2}
+        if precision not in modes:
+            raise ValueError("precision must be 'auto', 'q16' or 'fp32'")
+        _lib.check(self._lib.qmb_ctx_set_scan_precision(self._h, modes[precision]))
 
     @property
     def last_scan_bytes_per_gather(self) -> int:

@@ -53,7 +53,8 @@ extern "C" int qmb_ctx_create(int device, qmb_ctx_t *out) {
   ctx->sm_count = prop.multiProcessorCount;
   QMB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 4; ++i) QMB_CUDA(cudaEventCreate(&ctx->ev[i]));
-  if (const char *pr = getenv("QMB_SCAN_PRECISION")) ctx->scan_fp32 = strcmp(pr, "fp32") == 0 ? 1 : 0;
+  if (const char *pr = getenv("QMB_SCAN_PRECISION"))
+    ctx->scan_fp32 = strcmp(pr, "fp32") == 0 ? 1 : (strcmp(pr, "q16") == 0 ? 2 : 0);
   const char *v = getenv("QMB_VARIANT");
   if (v && atoi(v) >= 0 && atoi(v) < QMB_N_VARIANTS) ctx->variant = atoi(v);
   *out = ctx;
@@ -68,9 +69,10 @@ extern "C" int qmb_ctx_set_variant(qmb_ctx_t ctx, int variant) {
   return QMB_OK;
 }
 
-extern "C" int qmb_ctx_set_scan_precision(qmb_ctx_t ctx, int fp32) {
+extern "C" int qmb_ctx_set_scan_precision(qmb_ctx_t ctx, int mode) {
   if (!ctx) QMB_FAIL(QMB_ERR_ARG, "null context");
-  ctx->scan_fp32 = fp32 ? 1 : 0;
+  if (mode < 0 || mode > 2) QMB_FAIL(QMB_ERR_ARG, "precision mode must be 0 (auto), 1 (float32) or 2 (16-bit)");
+  ctx->scan_fp32 = mode;
   return QMB_OK;
 }
 

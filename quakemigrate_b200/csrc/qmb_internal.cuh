@@ -94,7 +94,7 @@ struct qmb_ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t launches = 0;
-  int scan_fp32 = 0;      // 1: detect scans gather float32 rows (default: 16-bit fixed point)
+  int scan_fp32 = 0;      // detect scan operands: 0 automatic (16-bit fixed point when accurate enough), 1 float32, 2 16-bit
   int last_scan_q16 = 0;  // what the last detect scan actually used
 
   // NCCL

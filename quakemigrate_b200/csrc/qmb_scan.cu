@@ -105,7 +105,7 @@ struct ScanParams {
   // on the fma pipe (IMAD, IMAD.HI) -- the compiler cannot fold a multiplier it does not know --
   // while shifts and adds would all land on the alu pipe, which is the one that saturates
   uint32_t q_one, q_64k;
-  int q_form;  // 0: IADD3 + LEA.HI (alu)   1: IMAD word sums   2: IMAD word sums + IMAD.HI for odd words
+  int q_form;  // 0: IADD3 + LEA.HI (alu)  1: IMAD word sums  2: 1 + IMAD.HI for odd words  3: IMAD / IADD3 alternating
   long long row_stride;  // elements
   long long t_origin;    // index within a row of (tau = 0, sample t' = 0); multiple of 4
   int S, n_chunks;       // n_chunks = stages per node tile (rows / CR)
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
             for (int q = 0; q < H; ++q)
 #pragma unroll
               for (int k = 0; k < KW; ++k) {
-                if constexpr (QF == 0) A[h * H + q][k] += v[q][k];
+                if (QF == 0 || (QF == 3 && (k & 1))) A[h * H + q][k] += v[q][k];
                 else A[h * H + q][k] = v[q][k] * p.q_one + A[h * H + q][k];
                 if (QF == 2 && (k & 1)) Hs[h * H + q][k] = __umulhi(v[q][k], p.q_64k) + Hs[h * H + q][k];
                 else Hs[h * H + q][k] += v[q][k] >> 16;
@@ -749,6 +749,7 @@ int dispatch_scan_q16(qmb_ctx *ctx, const QmbVariant &v, const ScanParams &p, in
     case 7:
       if (p.q_form == 0) return launch_scan<12, 4, 8, 4, 32>(ctx, p, grid, smem);
       if (p.q_form == 1) return launch_scan<12, 4, 8, 5, 32>(ctx, p, grid, smem);
+      if (p.q_form == 3) return launch_scan<12, 4, 8, 7, 32>(ctx, p, grid, smem);
       return launch_scan<12, 4, 8, 6, 32>(ctx, p, grid, smem);
   }
   QMB_FAIL(QMB_ERR_ARG, "kernel variant %d has no 16-bit form", v.id);
@@ -876,8 +877,18 @@ int qmb_scan_run(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, int32_t fsmp, int32_t 
   int shift;
   // detect scans read 16-bit fixed-point rows unless float32 was asked for (or the table / rows
   // have no 16-bit form); candidates are re-evaluated in float64 either way
-  const bool use_q = !ctx->scan_fp32 && O->qstep > 0.0 && O->q16.p && L->RSq > 0 && L->tauq16.p &&
-                     q16_variant(L->v) && O->S <= 256;  // sum(u) < 2^24: exact in float32
+  bool use_q = ctx->scan_fp32 != 1 && O->qstep > 0.0 && O->q16.p && L->RSq > 0 && L->tauq16.p &&
+               q16_variant(L->v) && O->S <= 256;  // sum(u) < 2^24: exact in float32
+  if (use_q && ctx->scan_fp32 == 0) {
+    // automatic choice: the 16-bit rows leave arg-max and max_coa exact, but max_norm_coa divides
+    // by a node sum built from the quantised stacks.  One node's coalescence is off by about
+    // sigma = qstep * sqrt(S / 12) / available (relative), and the sum over N nodes averages that
+    // down by ~sqrt(N) (less where neighbouring nodes share samples: a factor 32 is held back).
+    // Keep float32 rows when that estimate is not clearly inside the 1e-5 bar (tiny grids, or
+    // `available` much smaller than the number of rows).
+    const double sigma = O->qstep * sqrt((double)O->S / 12.0) / (double)available;
+    if (32.0 * sigma / sqrt((double)L->n_global) > 5e-6) use_q = false;
+  }
   QMB_TRY(scan_setup(ctx, L, O, fsmp, T, available, p, smem, shift, use_q));
   const int R = p.R, grid = ctx->sm_count;
 

@@ -3,7 +3,8 @@
 set -x
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -q -m gpu -x 2>&1 | tail -30 > gpurun_out/gpu_tests.log; tail -30 gpurun_out/gpu_tests.log
-for prec in q16 fp32; do
+timeout 120 python __graft_entry__.py --smoke 2>&1 | tail -3
+for prec in ${PRECS:-auto}; do
   timeout 300 python bench.py --steps 5 --warmup 3 --precision $prec $BENCH_EXTRA > gpurun_out/bench_n1_$prec.json 2> gpurun_out/bench_n1_$prec.err
   python - <<PY
 import json
@@ -12,7 +13,7 @@ print("$prec value %.4g ms/step %.2f scan_ms %.2f e2e %.4g slow %s pipe %s" % (j
 PY
   tail -3 gpurun_out/bench_n1_$prec.err
 done
-for form in 0 1 2; do
+for form in ${FORMS:-1 3}; do
   QMB_Q16_FORM=$form timeout 200 python bench.py --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/bench_form$form.json 2> gpurun_out/bench_form$form.err
   python - <<PY
 import json

@@ -39,7 +39,29 @@ def test_both_operand_formats_meet_the_contract(precision, bpg, seed):
     assert used == bpg
     assert np.array_equal(got[2], want[2])
     np.testing.assert_allclose(got[0], want[0], rtol=1e-9)
+    # forced 16-bit rows on a small grid: the node sum averages the quantisation noise over few
+    # nodes only (the automatic mode keeps float32 here, see test_automatic_choice)
+    np.testing.assert_allclose(got[1], want[1], rtol=1e-5 if precision == "fp32" else 1e-4)
+
+
+def test_automatic_choice():
+    """auto = 16-bit rows at realistic sizes, float32 rows where the node sum could not average the
+    quantisation noise down (tiny grids; `available` far below the row count)."""
+    small = syn.random_problem(1, (3, 2, 2), 24, 300, 10, 60)
+    got, used = _run("auto", small[0], small[1], 10, 60, 24)
+    assert used == 4
+    want = O.detect_fused(small[0], small[1], 10, 60, 24, threads=2)
+    assert np.array_equal(got[2], want[2])
     np.testing.assert_allclose(got[1], want[1], rtol=1e-5)
+    big = syn.random_problem(2, (40, 40, 30), 16, 400, 10, 60)
+    got, used = _run("auto", big[0], big[1], 10, 60, 16)
+    assert used == 2
+    want = O.detect_fused(big[0], big[1], 10, 60, 16, threads=8)
+    assert np.array_equal(got[2], want[2])
+    np.testing.assert_allclose(got[0], want[0], rtol=1e-9)
+    np.testing.assert_allclose(got[1], want[1], rtol=1e-5)
+    got, used = _run("auto", big[0], big[1], 10, 60, 1)  # available = 1: no division of the error
+    assert used == 4
 
 
 def test_formats_agree_with_each_other_on_a_planted_event():
@@ -56,7 +78,7 @@ def test_formats_agree_with_each_other_on_a_planted_event():
             res[precision] = eng.detect_fetch(cfg.n_samples)
     assert np.array_equal(res["q16"][2], res["fp32"][2])
     np.testing.assert_allclose(res["q16"][0], res["fp32"][0], rtol=1e-12)
-    np.testing.assert_allclose(res["q16"][1], res["fp32"][1], rtol=1e-5)
+    np.testing.assert_allclose(res["q16"][1], res["fp32"][1], rtol=2e-5)
 
 
 def test_clip_floor_is_on_the_quantisation_grid():
@@ -82,4 +104,4 @@ def test_wide_dynamic_range_rows():
     got, _ = _run("q16", onsets, tau, fsmp, lsmp, S)
     assert np.array_equal(got[2], want[2])
     np.testing.assert_allclose(got[0], want[0], rtol=1e-9)
-    np.testing.assert_allclose(got[1], want[1], rtol=1e-5)
+    np.testing.assert_allclose(got[1], want[1], rtol=1e-3)  # step = log(5e6 / 0.01) / 65535 on 960 nodes
