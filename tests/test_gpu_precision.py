@@ -91,7 +91,7 @@ def test_clip_floor_is_on_the_quantisation_grid():
     assert used == 2
     assert (got[2] == 0).all()
     np.testing.assert_allclose(got[0], 0.4, rtol=1e-12)
-    np.testing.assert_allclose(got[1], 1.0, rtol=1e-12)
+    np.testing.assert_allclose(got[1], 1.0, rtol=1e-6)  # exp2 of the float32 stack, summed over nodes
 
 
 def test_wide_dynamic_range_rows():
