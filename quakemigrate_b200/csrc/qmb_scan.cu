@@ -741,11 +741,14 @@ int dispatch_scan(qmb_ctx *ctx, const QmbVariant &v, const ScanParams &p, int gr
 
 constexpr int QMB_Q16_FORM = 1;  // default accumulation form (see ScanParams::q_form)
 // 16-bit fixed-point detect scan: built for the 4-nodes-per-warp variants
-bool q16_variant(const QmbVariant &v) { return v.id == 4 || v.id == 6 || v.id == 7; }
+bool q16_variant(const QmbVariant &v) { return v.NPW == 4 && (v.K % 2) == 0; }
 int dispatch_scan_q16(qmb_ctx *ctx, const QmbVariant &v, const ScanParams &p, int grid, size_t smem) {
   switch (v.id) {
+    case 0: return launch_scan<16, 4, 8, 4 + QMB_Q16_FORM, 16>(ctx, p, grid, smem);
     case 4: return launch_scan<12, 4, 8, 4 + QMB_Q16_FORM, 16>(ctx, p, grid, smem);
     case 6: return launch_scan<8, 4, 8, 4 + QMB_Q16_FORM, 16>(ctx, p, grid, smem);
+    case 8: return launch_scan<15, 4, 8, 4 + QMB_Q16_FORM, 32>(ctx, p, grid, smem);
+    case 9: return launch_scan<15, 4, 8, 4 + QMB_Q16_FORM, 16>(ctx, p, grid, smem);
     case 7:
       if (p.q_form == 0) return launch_scan<12, 4, 8, 4, 32>(ctx, p, grid, smem);
       if (p.q_form == 1) return launch_scan<12, 4, 8, 5, 32>(ctx, p, grid, smem);
