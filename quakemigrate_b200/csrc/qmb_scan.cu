@@ -74,26 +74,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-// Producer-side wait: the producer runs stages ahead and would otherwise spin on `empty` for most
-// of the kernel (measured: 5.5 % of all issued instructions were its TRYWAIT / BRA / YIELD loop,
-// in a kernel bound by instruction issue).  Back off between polls; a few hundred ns of extra
-// reaction time is nothing against the microseconds a stage lasts.
-__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
-  for (;;) {
-    uint32_t done;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) return;
-    __nanosleep(200);
-  }
-}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -207,7 +187,7 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
           for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
           total += tau_bytes + (c == 0 ? (uint32_t)NB * 4u : 0u);
           const uint32_t full = bar_base + 8u * st, empty = bar_base + 8u * (p.n_stages + st);
-          mbar_wait_backoff(empty, ph ^ 1u);
+          mbar_wait(empty, ph ^ 1u);
           const uint32_t stage = smem_base + (uint32_t)st * p.stage_bytes;
           if (lane == 0) mbar_expect_tx(full, total);
           __syncwarp();
