@@ -221,7 +221,9 @@ class QuakeScan:
         ``device_output`` the COA / COA_N / Z channels are quantised on the device and only int32
         channels plus grid coordinates come back (``qmb_detect_fetch_quantised``); otherwise the
         float64 traces are fetched and quantised on the host like the reference.  Both give
-        byte-identical files.  Returns ``(ScanmSEED, [availability dict or None per step])``.
+        byte-identical files.  The station availability of every step goes to
+        ``<run>/detect/availability`` (io/availability.py:123-152).  Returns
+        ``(ScanmSEED, [availability dict or None per step])``.
         """
         from .scanmseed import ScanmSEED
 
@@ -256,6 +258,11 @@ class QuakeScan:
                 availability.append(None)
         if not coalescence.written:
             coalescence.write()
+        if any(a is not None for a in availability):  # scan.py:467
+            from .availability import write_availability
+            from .scanmseed import to_us
+            times = [to_us(starttime) + int(round(self.timestep * i * 1e6)) for i in range(len(availability))]
+            write_availability(run, times, availability)
         return coalescence, availability
 
     def close(self):

@@ -8,6 +8,8 @@ Run in the dev container (needs /root/reference):
                               examples/benchmarks/Icequake_Iceland/2014_180.scanmseed (the file
                               tests/test_benchmarks.py:80-105 compares detect() against): 5 channels
                               x 2500 samples, 11 STEIM-2 records written by obspy/libmseed
+  golden_2014_180_StationAvailability.csv   bit-identical copy of the availability file of the same
+                              run (tests/test_benchmarks.py:99-105 of the reference)
   golden_iceland_grid.json    node_count / node_spacing / ll_corner / PROJ strings of
                               examples/benchmarks/Icequake_Iceland/example.LUT
 
@@ -28,6 +30,7 @@ BENCH = pathlib.Path("/root/reference/examples/benchmarks/Icequake_Iceland")
 
 if __name__ == "__main__":
     shutil.copyfile(BENCH / "2014_180.scanmseed", HERE / "golden_2014_180.scanmseed")
+    shutil.copyfile(BENCH / "2014_180_StationAvailability.csv", HERE / "golden_2014_180_StationAvailability.csv")
     with open(BENCH / "example.LUT", "rb") as f:
         d = _StubUnpickler(f).load()
     meta = {

@@ -133,6 +133,10 @@ def test_continuous_compute_writes_the_same_file_either_way(tmp_path):
             coalescence, availability = scan.continuous_compute(t_first, chunks, run, device_output=mode)
             assert coalescence.written and availability[1] is None and sum(availability[0].values()) > 0
             files.append(run / "detect" / "scanmseed" / "2014_180.scanmseed")
+            av_file = run / "detect" / "availability" / "2014_180_StationAvailability.csv"
+            lines = av_file.read_text().splitlines()
+            assert len(lines) == 4 and lines[0].startswith(",ST000_P,") and lines[2].endswith(",0,0,0")
+            assert lines[1].startswith("2014-06-29T18:42:05.000000Z,1,")
         scan.close()
     assert files[0].read_bytes() == files[1].read_bytes()
     df, stats = sm.read_scanmseed(tmp_path / "dev", t_first, t_first + 12.0, 0.0, lut.unit_conversion_factor)

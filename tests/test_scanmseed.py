@@ -235,3 +235,33 @@ def test_scanmseed_continuous_write_and_steim1_fallback(tmp_path):
     assert {r["version"] for r in recs} == {1}  # the whole file fell back to STEIM-1 (:219-224)
     data, _ = sm.read_scanmseed(tmp_path, t0, t0 + dt.timedelta(seconds=9.9), 0.0, 1000.0)
     assert np.array_equal(data["Z"].values, coord[:, 2])
+
+
+def test_availability_file_roundtrip_bytes(tmp_path):
+    """read -> write reproduces the reference's golden StationAvailability.csv byte for byte
+    (pandas `to_csv` of a frame indexed by UTCDateTime, io/availability.py:123-152)."""
+    import shutil
+
+    from quakemigrate_b200 import availability as av
+
+    gold = GOLD / "golden_2014_180_StationAvailability.csv"
+    src = tmp_path / "a" / "detect" / "availability"
+    src.mkdir(parents=True)
+    shutil.copyfile(gold, src / "2014_180_StationAvailability.csv")
+    t0 = dt.datetime(2014, 6, 29, 18, 42, 5)
+    index, columns, table = av.read_availability(tmp_path / "a", t0, t0 + dt.timedelta(seconds=10))
+    assert index == [t0 + dt.timedelta(seconds=2.5 * i) for i in range(4)]  # timestep 2.5 s (iceland_detect.py)
+    assert columns[:2] == ["SKR01_P", "SKR02_P"] and columns[-1] == "SKG13_S" and table.shape == (4, 26)
+    assert table.sum(axis=1).tolist() == [24, 24, 24, 24]  # SKG09 is down: 24 of 26 rows (SURVEY 8, cfg 1)
+    rows = [dict(zip(columns, r)) for r in table]
+    files = av.write_availability(tmp_path / "b", index, rows)
+    assert [f.name for f in files] == ["2014_180_StationAvailability.csv"]
+    assert files[0].read_bytes() == gold.read_bytes()
+    # steps without data are rows of zeros; files split by day
+    times = [dt.datetime(2020, 12, 31, 23, 59, 0), dt.datetime(2021, 1, 1, 0, 1, 0)]
+    files = av.write_availability(tmp_path / "c", times, [None, rows[0]], columns=columns)
+    assert sorted(f.name for f in files) == ["2020_366_StationAvailability.csv", "2021_001_StationAvailability.csv"]
+    _, _, tab = av.read_availability(tmp_path / "c", times[0], times[1])
+    assert tab[0].sum() == 0 and tab[1].sum() == 24
+    with pytest.raises(av.NoStationAvailabilityDataException):
+        av.read_availability(tmp_path / "c", dt.datetime(2019, 1, 1), dt.datetime(2019, 1, 2))
