@@ -892,7 +892,11 @@ int qmb_scan_run(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, int32_t fsmp, int32_t 
     const double sigma = O->qstep * sqrt((double)O->S / 12.0) / (double)available;
     if (32.0 * sigma / sqrt((double)L->n_global) > 5e-6) use_q = false;
   }
-  QMB_TRY(scan_setup(ctx, L, O, fsmp, T, available, p, smem, shift, use_q));
+  if (use_q && scan_setup(ctx, L, O, fsmp, T, available, p, smem, shift, true) != QMB_OK) {
+    use_q = false;  // e.g. too few pipeline stages for the (slightly wider) 16-bit rows
+    p = ScanParams{};
+  }
+  if (!use_q) QMB_TRY(scan_setup(ctx, L, O, fsmp, T, available, p, smem, shift, false));
   const int R = p.R, grid = ctx->sm_count;
 
   const size_t n_part = (size_t)R * L->v.W * p.Tpad;
