@@ -265,3 +265,40 @@ def test_availability_file_roundtrip_bytes(tmp_path):
     assert tab[0].sum() == 0 and tab[1].sum() == 24
     with pytest.raises(av.NoStationAvailabilityDataException):
         av.read_availability(tmp_path / "c", dt.datetime(2019, 1, 1), dt.datetime(2019, 1, 2))
+
+
+def test_mseed_gaps_and_trimmed_reads(tmp_path):
+    """Records of one channel that do not follow each other become separate traces (obspy's
+    read + merge(method=-1) keeps gaps); starttime / endtime trim to the samples inside."""
+    sr = 128  # 7.8125 ms: record start times are not multiples of 0.1 ms (BTIME truncation)
+    rng = np.random.default_rng(4)
+    a = rng.integers(-50000, 50000, 5000).astype(np.int32)
+    b = rng.integers(-5, 5, 3000).astype(np.int32)
+    t0 = dt.datetime(2021, 3, 4, 5, 6, 7)
+    t1 = t0 + dt.timedelta(seconds=len(a) / sr + 10.0)  # a 10 s gap
+    file = tmp_path / "gappy.mseed"
+    sm.write_mseed(file, [sm.Trace(a, "COA", t0, sr), sm.Trace(b, "COA", t1, sr)])
+    got = sm.read_mseed(file)
+    assert len(got) == 2 and got[0].npts == 5000 and got[1].npts == 3000
+    assert np.array_equal(got[0].data, a) and np.array_equal(got[1].data, b)
+    assert got[0].starttime == t0 and abs((got[1].starttime - t1).total_seconds()) < 1e-4
+    # several records per trace were needed and their (truncated) start times still chain up
+    assert len(sm._parse_records(file.read_bytes())) > 2
+    # trimmed read: 2 s .. 4 s of the first trace, end inclusive
+    sub = sm.read_mseed(file, starttime=t0 + dt.timedelta(seconds=2), endtime=t0 + dt.timedelta(seconds=4))
+    assert len(sub) == 1 and sub[0].npts == 2 * sr + 1
+    assert np.array_equal(sub[0].data, a[2 * sr:4 * sr + 1])
+    # nothing inside the gap
+    assert sm.read_mseed(file, starttime=t0 + dt.timedelta(seconds=42), endtime=t0 + dt.timedelta(seconds=45)) == []
+
+
+def test_time_inputs():
+    us = sm.to_us(dt.datetime(2014, 6, 29, 18, 42, 5))
+    assert us == 1_404_067_325_000_000
+    assert sm.to_us(1_404_067_325.0) == us and sm.to_us(np.datetime64("2014-06-29T18:42:05")) == us
+    aware = dt.datetime(2014, 6, 29, 20, 42, 5, tzinfo=dt.timezone(dt.timedelta(hours=2)))
+    assert sm.to_us(aware) == us and sm.from_us(us) == dt.datetime(2014, 6, 29, 18, 42, 5)
+    with pytest.raises(TypeError):
+        sm.to_us("2014-06-29")
+    with pytest.raises(ValueError):
+        sm.write_mseed("/dev/null", [sm.Trace(np.zeros(4, np.int32), "COA", 0, 12.5)])
