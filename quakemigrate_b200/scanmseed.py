@@ -116,10 +116,30 @@ class Trace:
 
     def __init__(self, data, station, starttime, sampling_rate, network="NW", location="",
                  channel=""):
-        self.data = np.ascontiguousarray(data, dtype=np.int32)
+        self._chunks = [np.ascontiguousarray(data, dtype=np.int32)]
+        self._npts = int(self._chunks[0].size)
         self.station, self.network, self.location, self.channel = station, network, location, channel
         self.start_us = to_us(starttime)
         self.sampling_rate = float(sampling_rate)
+
+    @property
+    def data(self) -> np.ndarray:
+        """The samples; pieces appended with :meth:`extend` are joined on first use."""
+        if len(self._chunks) > 1:
+            self._chunks = [np.concatenate(self._chunks)]
+        return self._chunks[0]
+
+    @data.setter
+    def data(self, value):
+        self._chunks = [np.ascontiguousarray(value, dtype=np.int32)]
+        self._npts = int(self._chunks[0].size)
+
+    def extend(self, more: np.ndarray) -> None:
+        """Append samples without copying what is already there (a day of detect() appends
+        hundreds of timesteps; records of a file arrive one by one)."""
+        more = np.ascontiguousarray(more, dtype=np.int32)
+        self._chunks.append(more)
+        self._npts += int(more.size)
 
     @property
     def id(self):
@@ -127,7 +147,7 @@ class Trace:
 
     @property
     def npts(self):
-        return int(self.data.size)
+        return self._npts
 
     @property
     def delta_us(self):
@@ -278,7 +298,7 @@ def read_mseed(path, starttime=None, endtime=None):
             last = segs[-1]
             expect = last.time_of(last.npts)
             if abs(tr.start_us - expect) <= 0.5 * last.delta_us and last.sampling_rate == tr.sampling_rate:
-                last.data = np.concatenate([last.data, tr.data])
+                last.extend(tr.data)
                 continue
         segs.append(tr)
     out = []
@@ -377,7 +397,7 @@ class ScanmSEED:
             for old in reversed(self.stream):
                 if old.id == tr.id:
                     if abs(old.time_of(old.npts) - tr.start_us) <= 0.5 * old.delta_us:
-                        old.data = np.concatenate([old.data, tr.data])
+                        old.extend(tr.data)
                         tr = None
                     break
             if tr is not None:
