@@ -142,7 +142,7 @@ struct qmb_lut {
   int ntx = 0, nty = 0, ntz = 0, n_tiles = 0;
   int32_t max_tau = 0, max_span = 0;
   double dup_frac = 0.0;  // fraction of neighbouring nodes (inside a warp's group) sharing the row's offset
-  DevBuf<uint16_t> tau16;   // [n_tiles][Spad][NB]   tau - tmin4(tile,row)
+  DevBuf<uint16_t> tau16;   // [n_tiles][Spad][NB]   tau - tmin(tile,row)
   DevBuf<int32_t> tmin;     // [n_tiles][Spad]       multiple of 4
   DevBuf<uint16_t> span;    // [n_tiles][Spad]       max(tau16) within the tile
   DevBuf<uint32_t> nodeidx; // [n_tiles][NB]         global flat node index or 0xFFFFFFFF (pad)

@@ -9,7 +9,7 @@
 //   CTA       = persistent, one per SM; walks items  blockIdx.x, +gridDim.x, ...
 //   node tile = W*NPW spatially compact nodes (default 12*4 = 48: 4x4x3 boxes), laid out by qmb_lut.cu
 //   stage     = (node tile, chunk of CR onset rows): the producer warp bulk-copies, per row, the
-//               window [tmin4, tmin4 + span + 32K) of the float32 log-onset row into shared memory
+//               window [tmin, tmin + span + 32K) of the log-onset row (float32, or the two 16-bit streams) into shared memory
 //               (cp.async.bulk -> SASS UBLKCP, completion on an mbarrier) plus the tile's uint16
 //               tau offsets; a ring of stages decouples it from the W consumer warps.
 //   consumer  = warp w owns NPW nodes of the tile; LANES ARE TIME SAMPLES (lane l handles
