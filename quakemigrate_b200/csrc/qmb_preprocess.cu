@@ -415,6 +415,7 @@ int qmb_preprocess_device(qmb_ctx *ctx, const double *d_x, int64_t x_stride, con
     QMB_FAIL(QMB_ERR_UNSUPPORTED, "filters with %d second-order sections are not built (0..%d)", nsec, PP_MAX_SEC);
   if (nsec > 0 && !sos) QMB_FAIL(QMB_ERR_ARG, "null filter coefficients");
   if (decimate < 1) QMB_FAIL(QMB_ERR_ARG, "decimation factor must be >= 1");
+  if (n_sel > 65535) QMB_FAIL(QMB_ERR_UNSUPPORTED, "more than 65535 traces per call (%d): split the block", n_sel);
   if (taper_fraction < 0.0 || taper_fraction > 0.5) QMB_FAIL(QMB_ERR_ARG, "taper fraction must be in [0, 0.5]");
   const int D = 2 * nsec;
   PreParams p = {};
