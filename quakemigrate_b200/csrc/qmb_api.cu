@@ -55,7 +55,6 @@ extern "C" int qmb_ctx_create(int device, qmb_ctx_t *out) {
   for (int i = 0; i < 4; ++i) QMB_CUDA(cudaEventCreate(&ctx->ev[i]));
   if (const char *pr = getenv("QMB_SCAN_PRECISION"))
     ctx->scan_fp32 = strcmp(pr, "fp32") == 0 ? 1 : (strcmp(pr, "q16") == 0 ? 2 : 0);
-  if (const char *qf = getenv("QMB_Q16_FORM")) ctx->q16_quad = atoi(qf) == 4 ? 1 : 0;
   const char *v = getenv("QMB_VARIANT");
   if (v && atoi(v) >= 0 && atoi(v) < QMB_N_VARIANTS) ctx->variant = atoi(v);
   *out = ctx;
@@ -134,7 +133,7 @@ extern "C" int qmb_ctx_destroy(qmb_ctx_t ctx) {
   qmb_fft_release(ctx);
   if (ctx->tmp_onsets) {
     ctx->tmp_onsets->log32.release(); ctx->tmp_onsets->log64.release(); ctx->tmp_onsets->rowmax.release();
-    ctx->tmp_onsets->q16.release(); ctx->tmp_onsets->q16x4.release(); ctx->tmp_onsets->qrange.release();
+    ctx->tmp_onsets->q16.release(); ctx->tmp_onsets->qrange.release();
     delete ctx->tmp_onsets;
     ctx->tmp_onsets = nullptr;
   }
@@ -370,7 +369,7 @@ extern "C" int qmb_lut_free(qmb_lut_t L) {
   if (!L) return QMB_OK;
   cudaSetDevice(L->device);
   L->tau16.release(); L->tmin.release(); L->span.release(); L->nodeidx.release();
-  L->boxes.release(); L->slotmap.release(); L->tauq16.release(); L->tauq4.release();
+  L->boxes.release(); L->slotmap.release(); L->tauq16.release();
   delete L;
   return QMB_OK;
 }
@@ -392,7 +391,7 @@ extern "C" int qmb_lut_info(qmb_lut_t L, qmb_lut_info_t *info) {
 extern "C" int qmb_onsets_free(qmb_onsets_t O) {
   if (!O) return QMB_OK;
   cudaSetDevice(O->device);
-  O->log32.release(); O->log64.release(); O->rowmax.release(); O->q16.release(); O->q16x4.release(); O->qrange.release();
+  O->log32.release(); O->log64.release(); O->rowmax.release(); O->q16.release(); O->qrange.release();
   delete O;
   return QMB_OK;
 }

@@ -96,7 +96,6 @@ struct qmb_ctx {
   int64_t launches = 0;
   int scan_fp32 = 0;      // detect scan operands: 0 automatic (16-bit fixed point when accurate enough), 1 float32, 2 16-bit
   int last_scan_q16 = 0;  // what the last detect scan actually used
-  int q16_quad = 0;       // experimental (QMB_Q16_FORM=4): four phase-shifted 16-bit streams, one LDS.64 per four gather-adds
 
   // NCCL
   void *nccl_comm = nullptr;
@@ -154,9 +153,6 @@ struct qmb_lut {
   // "even" one); RSq = elements per staged stream
   DevBuf<uint16_t> tauq16;  // [n_tiles][Spad][NB]
   int32_t RSq = 0;
-  // four-stream form: offset in 8-byte units = (tau16 >> 2) + (tau16 & 3) * RSq4 / 4
-  DevBuf<uint16_t> tauq4;
-  int32_t RSq4 = 0;
 };
 
 struct qmb_ttgrids {  // every (station, phase) travel-time grid, float64 seconds, on the device
@@ -182,7 +178,6 @@ struct qmb_onsets {
   //   stream 1 ("odd") : q16[(2 s + 1) * qstride + pos] = u(sample + 1)
   // so that the pair (u(i), u(i + 1)) is one aligned 32-bit word for every i.
   DevBuf<uint16_t> q16;
-  DevBuf<uint16_t> q16x4;  // four streams u(i) .. u(i+3) per row (only with qmb_ctx::q16_quad)
   DevBuf<double> qrange;  // [S][2] min / max of each row
   int64_t qstride = 0, qfront = 0;
   double qmin = 0.0, qstep = 0.0;  // qstep == 0: no quantised copy (e.g. rows of the T1 migrate())

@@ -128,13 +128,11 @@ __global__ void __launch_bounds__(LT_THREADS) k_lut_tile(LutTileParams p) {
   }
 }
 
-// shift = 1: pairs (two streams, 4-byte units); shift = 2: quads (four streams, 8-byte units)
-__global__ void __launch_bounds__(256) k_lut_tauq(const uint16_t *tau16, uint16_t *tauq16, size_t n, int stream_units,
-                                                  int shift) {
+__global__ void __launch_bounds__(256) k_lut_tauq(const uint16_t *tau16, uint16_t *tauq16, size_t n, int half_words) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const unsigned t = tau16[i];
-  tauq16[i] = (uint16_t)((t >> shift) + (t & ((1u << shift) - 1u)) * (unsigned)stream_units);
+  tauq16[i] = (uint16_t)((t >> 1) + (t & 1u) * (unsigned)half_words);
 }
 
 }  // namespace
@@ -264,22 +262,9 @@ static int lut_build_variant(qmb_ctx *ctx, qmb_lut *L, const int32_t *d_raw, con
   if ((L->v.K & 1) == 0 && L->max_span / 2 + L->RSq / 2 < 65536) {
     const size_t n = (size_t)L->n_tiles * L->Spad * L->NB;
     QMB_TRY(L->tauq16.ensure(n));
-    k_lut_tauq<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(L->tau16.p, L->tauq16.p, n, L->RSq / 2, 1);
+    k_lut_tauq<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(L->tau16.p, L->tauq16.p, n, L->RSq / 2);
     ctx->launches++;
     QMB_CUDA(cudaGetLastError());
-    L->RSq4 = 0;
-    if (ctx->q16_quad) {
-      const int TT = 32 * L->v.K;
-      L->RSq4 = ((L->max_span + TT + 3 + 7) & ~7) + 8;
-      if (L->max_span / 4 + 3 * (L->RSq4 / 4) < 65536) {
-        QMB_TRY(L->tauq4.ensure(n));
-        k_lut_tauq<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(L->tau16.p, L->tauq4.p, n, L->RSq4 / 4, 2);
-        ctx->launches++;
-        QMB_CUDA(cudaGetLastError());
-      } else {
-        L->RSq4 = 0;
-      }
-    }
   } else {
     L->RSq = 0;
     L->tauq16.release();

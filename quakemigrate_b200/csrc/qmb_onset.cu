@@ -257,8 +257,7 @@ __global__ void __launch_bounds__(256) k_onset_range(const double *log64, long l
 // u(pos - qfront) in the even stream and u(pos - qfront + 1) in the odd stream.
 __global__ void __launch_bounds__(256) k_onset_quantise(const double *log64, long long stride, long long front,
                                                         long long P, uint16_t *q16, long long qstride,
-                                                        long long qfront, double qmin, double inv_step,
-                                                        int n_streams) {
+                                                        long long qfront, double qmin, double inv_step) {
   const int s = blockIdx.y;
   const long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (pos >= qstride) return;
@@ -269,8 +268,8 @@ __global__ void __launch_bounds__(256) k_onset_quantise(const double *log64, lon
     return (uint16_t)fmin(fmax(u, 0.0), 65535.0);
   };
   const long long i = pos - qfront;
-  for (int ph = 0; ph < n_streams; ++ph)  // stream ph holds u(sample + ph)
-    q16[((size_t)n_streams * s + ph) * qstride + pos] = quant(i + ph);
+  q16[((size_t)2 * s + 0) * qstride + pos] = quant(i);
+  q16[((size_t)2 * s + 1) * qstride + pos] = quant(i + 1);
 }
 
 }  // namespace
@@ -301,16 +300,9 @@ int qmb_onsets_quantise(qmb_ctx *ctx, qmb_onsets *O) {
   QMB_TRY(O->q16.ensure((size_t)2 * O->S * O->qstride));
   dim3 grid((unsigned)((O->qstride + 255) / 256), (unsigned)O->S);
   k_onset_quantise<<<grid, 256, 0, ctx->stream>>>(O->log64.p, O->stride, O->front, O->P, O->q16.p, O->qstride,
-                                                  O->qfront, O->qmin, 1.0 / O->qstep, 2);
+                                                  O->qfront, O->qmin, 1.0 / O->qstep);
   ctx->launches++;
   QMB_CUDA(cudaGetLastError());
-  if (ctx->q16_quad) {
-    QMB_TRY(O->q16x4.ensure((size_t)4 * O->S * O->qstride));
-    k_onset_quantise<<<grid, 256, 0, ctx->stream>>>(O->log64.p, O->stride, O->front, O->P, O->q16x4.p, O->qstride,
-                                                    O->qfront, O->qmin, 1.0 / O->qstep, 4);
-    ctx->launches++;
-    QMB_CUDA(cudaGetLastError());
-  }
   return QMB_OK;
 }
 

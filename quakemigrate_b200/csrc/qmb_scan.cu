@@ -177,13 +177,12 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
           int tmin = 0, len = 0;
           if (act) {
             tmin = p.tmin[(size_t)j * p.Spad + s];
-            if constexpr (MODE == 8) len = ((int)p.span[(size_t)j * p.Spad + s] + TT + 3 + 7) & ~7;
-            else if constexpr (MODE >= 4) len = ((int)p.span[(size_t)j * p.Spad + s] + TT + 2 + 7) & ~7;
+            if constexpr (MODE >= 4) len = ((int)p.span[(size_t)j * p.Spad + s] + TT + 2 + 7) & ~7;
             else len = ((int)p.span[(size_t)j * p.Spad + s] + TT + 3) & ~3;
           }
           // MODE 4: `bytes` per stream (2 bytes per sample), two streams per row
           uint32_t bytes = MODE >= 4 ? (uint32_t)len * 2u : (uint32_t)len * 4u;
-          uint32_t total = MODE == 8 ? 4u * bytes : (MODE >= 4 ? 2u * bytes : bytes);
+          uint32_t total = MODE >= 4 ? 2u * bytes : bytes;
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
           total += tau_bytes + (c == 0 ? (uint32_t)NB * 4u : 0u);
@@ -194,17 +193,10 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
           __syncwarp();
           if constexpr (MODE >= 4) {
             if (act) {
+              const uint16_t *src = p.on16 + (size_t)2 * s * p.row_stride + tbase + tmin;
               const uint32_t dst = stage + (uint32_t)lane * p.RS * 4u;
-              if constexpr (MODE == 8) {  // four streams u(i) .. u(i+3), RS / 2 elements each
-                const uint16_t *src = p.on16 + (size_t)4 * s * p.row_stride + tbase + tmin;
-#pragma unroll
-                for (int ph = 0; ph < 4; ++ph)
-                  bulk_g2s(dst + (uint32_t)ph * (uint32_t)p.RS, src + (size_t)ph * p.row_stride, bytes, full);
-              } else {
-                const uint16_t *src = p.on16 + (size_t)2 * s * p.row_stride + tbase + tmin;
-                bulk_g2s(dst, src, bytes, full);                                       // pairs (2i, 2i+1)
-                bulk_g2s(dst + (uint32_t)p.RS * 2u, src + p.row_stride, bytes, full);  // pairs (2i+1, 2i+2)
-              }
+              bulk_g2s(dst, src, bytes, full);                                       // pairs (2i, 2i+1)
+              bulk_g2s(dst + (uint32_t)p.RS * 2u, src + p.row_stride, bytes, full);  // pairs (2i+1, 2i+2)
             }
           } else if (act) {
             bulk_g2s(stage + (uint32_t)lane * p.RS * 4u, p.on32 + (size_t)s * p.row_stride + tbase + tmin,
@@ -240,11 +232,7 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
     }
 
     if constexpr (MODE >= 4) {
-      // MODE 8 (experimental): four phase-shifted streams per row, so that the four samples
-      // 128 kk + 4 l .. + 3 of a node are one aligned 8-byte unit: one LDS.64 per four gather-adds.
-      constexpr bool QUAD = MODE == 8;
-      constexpr int QF = QUAD ? 1 : MODE - 4;
-      static_assert(!QUAD || (K % 4) == 0, "four-stream form needs K % 4 == 0");
+      constexpr int QF = MODE - 4;
       // ---- 16-bit fixed-point rows: lane l owns the sample PAIRS (64 kk + 2 l, + 1), kk < K/2.
       // One LDS.32 fetches both samples of a pair (half the shared-memory bytes per gather-add);
       // A accumulates the whole words, Hs their upper halves: sum(lo) = A - (Hs << 16) exactly
@@ -270,7 +258,7 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
           }
           const int nrows = min(CR, p.S - c * CR);
           const uint32_t tau_addr = stage + rows_bytes + (uint32_t)(warp * NPW) * 2u;
-          uint32_t row_addr = stage + (uint32_t)lane * (QUAD ? 8u : 4u);
+          uint32_t row_addr = stage + (uint32_t)lane * 4u;
           auto load_off = [&](int sl, uint32_t (&off)[NPW]) {
             uint32_t a, b;
             asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(tau_addr + (uint32_t)sl * NB * 2u));
@@ -279,19 +267,10 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
           auto load_half = [&](int h, const uint32_t (&off)[NPW], uint32_t base, uint32_t (&v)[H][KW]) {
 #pragma unroll
             for (int q = 0; q < H; ++q) {
-              if constexpr (QUAD) {
-                const uint32_t a = base + off[h * H + q] * 8u;
+              const uint32_t a = base + off[h * H + q] * 4u;
 #pragma unroll
-                for (int k = 0; k < KW / 2; ++k)
-                  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];"
-                               : "=r"(v[q][2 * k]), "=r"(v[q][2 * k + 1])
-                               : "r"(a + 256u * k));
-              } else {
-                const uint32_t a = base + off[h * H + q] * 4u;
-#pragma unroll
-                for (int k = 0; k < KW; ++k)
-                  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v[q][k]) : "r"(a + 128u * k));
-              }
+              for (int k = 0; k < KW; ++k)
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v[q][k]) : "r"(a + 128u * k));
             }
           };
           auto add_half = [&](int h, const uint32_t (&v)[H][KW]) {
@@ -327,8 +306,7 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
           if (lane == 0) mbar_arrive(empty);
           if (++st == p.n_stages) { st = 0; ph ^= 1u; }
         }
-        // ---- per-tile epilogue: slot k = 2 kk + h <-> sample 64 kk + 2 lane + h
-        //      (four-stream form: word kk = 2 u + j <-> samples 128 u + 4 lane + 2 j + h) ---------
+        // ---- per-tile epilogue: slot k = 2 kk + h <-> sample 64 kk + 2 lane + h ---------------
 #pragma unroll
         for (int kk = 0; kk < KW; ++kk) {
           float e0 = 0.f, e1 = 0.f;
@@ -358,22 +336,6 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
         }
       }
       // ---- item done: publish (pairs of neighbouring samples -> 8 / 16-byte stores) -----------
-      if constexpr (QUAD) {
-        const size_t base4 = ((size_t)r * W + warp) * p.Tpad + (size_t)tt * TT + 4u * lane;
-#pragma unroll
-        for (int u = 0; u < KW / 2; ++u) {
-          const size_t o = base4 + 128u * u;
-          const int k0 = 4 * u;
-          *reinterpret_cast<float4 *>(p.pm1 + o) = make_float4(m1[k0], m1[k0 + 1], m1[k0 + 2], m1[k0 + 3]);
-          *reinterpret_cast<float4 *>(p.pm2 + o) = make_float4(m2[k0], m2[k0 + 1], m2[k0 + 2], m2[k0 + 3]);
-          *reinterpret_cast<float4 *>(p.pm3 + o) = make_float4(m3[k0], m3[k0 + 1], m3[k0 + 2], m3[k0 + 3]);
-          *reinterpret_cast<uint4 *>(p.pi1 + o) = make_uint4(i1[k0], i1[k0 + 1], i1[k0 + 2], i1[k0 + 3]);
-          *reinterpret_cast<uint4 *>(p.pi2 + o) = make_uint4(i2[k0], i2[k0 + 1], i2[k0 + 2], i2[k0 + 3]);
-          *reinterpret_cast<double2 *>(p.psum + o) = make_double2(sum[k0], sum[k0 + 1]);
-          *reinterpret_cast<double2 *>(p.psum + o + 2) = make_double2(sum[k0 + 2], sum[k0 + 3]);
-        }
-        continue;
-      }
       const size_t base = ((size_t)r * W + warp) * p.Tpad + (size_t)tt * TT + 2u * lane;
 #pragma unroll
       for (int kk = 0; kk < KW; ++kk) {
@@ -783,9 +745,7 @@ bool q16_variant(const QmbVariant &v) { return v.NPW == 4 && (v.K % 2) == 0; }
 int dispatch_scan_q16(qmb_ctx *ctx, const QmbVariant &v, const ScanParams &p, int grid, size_t smem) {
   switch (v.id) {
     case 0: return launch_scan<16, 4, 8, 4 + QMB_Q16_FORM, 16>(ctx, p, grid, smem);
-    case 4:
-      if (p.q_form == 4) return launch_scan<12, 4, 8, 8, 16>(ctx, p, grid, smem);
-      return launch_scan<12, 4, 8, 4 + QMB_Q16_FORM, 16>(ctx, p, grid, smem);
+    case 4: return launch_scan<12, 4, 8, 4 + QMB_Q16_FORM, 16>(ctx, p, grid, smem);
     case 6: return launch_scan<8, 4, 8, 4 + QMB_Q16_FORM, 16>(ctx, p, grid, smem);
     case 8: return launch_scan<15, 4, 8, 4 + QMB_Q16_FORM, 32>(ctx, p, grid, smem);
     case 9: return launch_scan<15, 4, 8, 4 + QMB_Q16_FORM, 16>(ctx, p, grid, smem);
@@ -826,15 +786,6 @@ static int scan_setup(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, long long first, 
     p.q_64k = 65536u;
     p.q_form = QMB_Q16_FORM;
     if (const char *f = getenv("QMB_Q16_FORM")) p.q_form = atoi(f);
-    if (p.q_form == 4) {  // experimental four-stream form: only where its data were built
-      if (ctx->q16_quad && L->v.id == 4 && L->RSq4 > 0 && L->tauq4.p && O->q16x4.p) {
-        p.on16 = O->q16x4.p;
-        p.tau16 = L->tauq4.p;
-        p.RS = 2 * L->RSq4;  // a staged row is four streams of RSq4 elements = RS * 4 bytes
-      } else {
-        p.q_form = QMB_Q16_FORM;
-      }
-    }
   }
   const int shift = (int)((front + first) & align);  // time tiles start `shift` samples early
   shift_out = shift;
