@@ -146,3 +146,16 @@ class StandInEngine:
         m4 = O.migrate(onsets.lin, lut.tau, fsmp, lsmp, available, threads=2)[..., win0:win1]
         coa = m4.sum(axis=-1)
         return (coa, m4) if return_map4d else coa
+
+    # -- locate, 3-D map stage (include/qmb200.h: qmb_gaufilt3d / qmb_map3d_peak / qmb_covfit3d) ---
+    def gaufilt3d(self, map3d, sgm=0.8):
+        return O.np_gaufilt3d(np.asarray(map3d, dtype=float), sgm)
+
+    def map_peak(self, map3d):
+        m = np.asarray(map3d, dtype=float)
+        ijk = tuple(int(i) for i in np.unravel_index(np.nanargmax(m), m.shape))
+        return ijk, float(np.nanmax(m)), float(np.nanmean(m))
+
+    def covfit3d(self, map3d, node_spacing, thresh=0.90, win=None):
+        assert not win, "windowed form is exercised on the GPU only"
+        return O.np_covfit3d(np.asarray(map3d, dtype=float), np.broadcast_to(node_spacing, (3,)), thresh)

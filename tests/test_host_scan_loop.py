@@ -143,3 +143,41 @@ def test_error_paths():
         scan._compute(_chunk(channels, 0, int((pre + post) * SR) - 5, 0.0))
     with pytest.raises(TypeError):
         QuakeScan(lut, object())
+
+
+def test_compute_locate_window_and_location(tmp_path):
+    """compute_locate (io/event.py:421-439 window, scan.py:696-733 fits): the marginal window sits
+    around the peak of max_coa, the map is the window's time-sum, and a planted source is found."""
+    from quakemigrate_b200.scan import marginal_window_indices
+
+    lut, channels = _setup(n_sta=4, grid=(9, 8, 6), seconds=40.0, seed=3)
+    # plant an impulsive arrival from node (5, 3, 2) at t0 = 20 s on every channel
+    src = (5, 3, 2)
+    t0 = 20.0
+    for st, comps in channels.items():
+        for c, v in comps.items():
+            tt = lut[st]["P" if c == "Z" else "S"][src]
+            k = int(round((t0 + tt) * SR))
+            v[k:k + 25] += 4000.0 * np.hanning(25) * np.sin(np.arange(25))
+    eng = StandInEngine()
+    onset = STALTAOnset(engine=eng, sampling_rate=SR, position="centred")
+    scan = QuakeScan(lut, onset, engine=eng, marginal_window=1.0, serve_on_device=False)
+    pre, post = scan.set_pads(20.0)
+    o = int(round((10.0 - pre) * SR))
+    n = int(round((pre + post + 20.0) * SR))
+    data = _chunk(channels, o, n, 10.0 - pre)
+    out = scan.compute_locate(data, return_map4d=True, fit_location=True)
+    i0, i1 = out["window"]
+    imax = out["peak_sample"]
+    assert (i0, i1, imax) == marginal_window_indices(out["max_coa"], 1.0, SR)
+    assert abs(out["times"][imax] - t0) < 0.2 and i1 - i0 == 2 * SR  # end-exclusive slice of 2 s + 1 sample
+    assert out["map4d"].shape == tuple(lut.node_count) + (i1 - i0,)
+    np.testing.assert_allclose(out["coa_map"], out["map4d"].sum(axis=-1), rtol=1e-12)
+    peak = np.unravel_index(np.argmax(out["coa_map"]), out["coa_map"].shape)
+    assert max(abs(a - b) for a, b in zip(peak, src)) <= 1
+    loc = out["location"]
+    want_xyz = lut.index2coord([list(src)])[0]
+    for key in ("spline", "gaussian", "covariance"):
+        xyz = loc[key] if key == "spline" else loc[key][0]
+        assert np.abs(np.asarray(xyz) - want_xyz).max() < 1.0  # within two nodes (0.5 km spacing)
+    scan.close()
