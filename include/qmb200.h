@@ -104,6 +104,27 @@ int qmb_ctx_set_variant(qmb_ctx_t ctx, int nodes_per_warp);
  * detect scan moved per gathered operand (2 or 4 bytes). */
 int qmb_ctx_set_scan_precision(qmb_ctx_t ctx, int mode);
 int qmb_ctx_last_scan_bytes_per_gather(qmb_ctx_t ctx, int *bytes);
+/* What the last detect scan did.  The 16-bit scan is VERIFIED per call: after the scan, 1-2 windows
+ * of 248 samples are re-scanned over all local nodes with float32 rows and the per-sample node sums
+ * (the denominator of max_norm_coa, migratelib.c:108) are compared; check_max_rel_err is the worst
+ * relative difference seen on any rank.  In the automatic mode a difference above 2e-6 discards the
+ * 16-bit result and the whole scan is redone with float32 rows (fell_back_fp32 = 1), so that
+ * max_norm_coa stays inside the 1e-5 bar also on inputs whose quantisation residuals are correlated.
+ * two_candidate_samples: samples whose two leading nodes were re-evaluated in float64;
+ * slow_path_samples: samples re-scanned over all nodes in float64 (>= 3 candidates inside the band). */
+typedef struct {
+  int32_t operand_bytes;  /* 2: 16-bit fixed-point rows, 4: float32 rows (what produced the result) */
+  int32_t fell_back_fp32;
+  int32_t check_windows, check_samples;
+  double check_max_rel_err;
+  int32_t slow_path_samples, two_candidate_samples;
+  float scan_ms, tail_ms, total_ms, check_ms; /* CUDA-event times: scan kernel, everything after it
+                                                 (merge, exchange, candidates, slow path, check), both,
+                                                 and the check windows alone (part of tail_ms) */
+  int32_t host_syncs_in_timed_region; /* cudaStreamSynchronize calls between the first and last event */
+  int32_t reserved;
+} qmb_scan_info_t;
+int qmb_ctx_last_scan_info(qmb_ctx_t ctx, qmb_scan_info_t *info);
 /* number of launches of this library's own kernels since context creation */
 int qmb_ctx_launch_count(qmb_ctx_t ctx, int64_t *count);
 
@@ -281,6 +302,27 @@ int qmb_locate_window(qmb_ctx_t ctx, qmb_lut_t lut, qmb_onsets_t onsets, int32_t
  *                 out12[0..2] = weighted expectation (index * spacing), out12[3..11] = covariance. */
 int qmb_gaufilt3d(qmb_ctx_t ctx, const double *map3d, int32_t nx, int32_t ny, int32_t nz, double sgm,
                   double *smoothed);
+/* The same stage on maps that never leave the device (QuakeScan._calculate_location,
+ * scan.py:696-733): qmb_locate_window_device leaves the marginal sum of the window in a map handle;
+ * normalise = map / nanmax(map) (scan.py:721); gaufilt returns a new handle; peak_device returns
+ * nanargmax / nanmax / nanmean (32 bytes); window copies a small box (the 5^3 spline and 7^3
+ * Gaussian-fit windows, scan.py:1045-1070) to the host; covfit returns the 12 moments.  A located
+ * event moves a few KB over PCIe instead of six copies of the 8*N-byte map. */
+typedef struct qmb_map3d *qmb_map3d_t;
+int qmb_locate_window_device(qmb_ctx_t ctx, qmb_lut_t lut, qmb_onsets_t onsets, int32_t fsmp,
+                             int32_t lsmp, int32_t available, int32_t win0, int32_t win1,
+                             qmb_map3d_t *coa_map);
+int qmb_map3d_upload(qmb_ctx_t ctx, const double *map3d, int32_t nx, int32_t ny, int32_t nz,
+                     qmb_map3d_t *out);
+int qmb_map3d_fetch(qmb_map3d_t map, double *host);
+int qmb_map3d_free(qmb_map3d_t map);
+int qmb_map3d_normalise(qmb_ctx_t ctx, qmb_map3d_t map);
+int qmb_map3d_gaufilt(qmb_ctx_t ctx, qmb_map3d_t map, double sgm, qmb_map3d_t *out);
+int qmb_map3d_peak_device(qmb_ctx_t ctx, qmb_map3d_t map, int64_t *argmax, double *maxval, double *mean);
+int qmb_map3d_window(qmb_ctx_t ctx, qmb_map3d_t map, int32_t x0, int32_t x1, int32_t y0, int32_t y1,
+                     int32_t z0, int32_t z1, double *host);
+int qmb_map3d_covfit(qmb_ctx_t ctx, qmb_map3d_t map, const double *spacing, double thresh, int32_t win,
+                     double *out12);
 int qmb_map3d_peak(qmb_ctx_t ctx, const double *map3d, int64_t n, int64_t *argmax, double *maxval,
                    double *mean);
 int qmb_covfit3d(qmb_ctx_t ctx, const double *map3d, int32_t nx, int32_t ny, int32_t nz,

@@ -47,6 +47,16 @@ class LutInfo(ctypes.Structure):
                 ("duplicate_fraction", c_double), ("variant", c_int32), ("reserved", c_int32)]
 
 
+class ScanInfo(ctypes.Structure):
+    """``qmb_scan_info_t`` (include/qmb200.h)."""
+    _fields_ = [("operand_bytes", c_int32), ("fell_back_fp32", c_int32), ("check_windows", c_int32),
+                ("check_samples", c_int32), ("check_max_rel_err", c_double),
+                ("slow_path_samples", c_int32), ("two_candidate_samples", c_int32),
+                ("scan_ms", ctypes.c_float), ("tail_ms", ctypes.c_float), ("total_ms", ctypes.c_float),
+                ("check_ms", ctypes.c_float), ("host_syncs_in_timed_region", c_int32),
+                ("reserved", c_int32)]
+
+
 class QmbError(RuntimeError):
     """A T2 entry point returned a non-zero status (message from ``qmb_last_error``)."""
 
@@ -74,6 +84,7 @@ SIGNATURES = {
     "qmb_ctx_set_variant": (ctypes.c_int, [c_void_p, ctypes.c_int]),
     "qmb_ctx_set_scan_precision": (ctypes.c_int, [c_void_p, ctypes.c_int]),
     "qmb_ctx_last_scan_bytes_per_gather": (ctypes.c_int, [c_void_p, ctypes.POINTER(ctypes.c_int)]),
+    "qmb_ctx_last_scan_info": (ctypes.c_int, [c_void_p, ctypes.POINTER(ScanInfo)]),
     "qmb_ctx_launch_count": (ctypes.c_int, [c_void_p, ctypes.POINTER(c_int64)]),
     "qmb_ctx_flush_l2": (ctypes.c_int, [c_void_p]),
     "qmb_host_register": (ctypes.c_int, [c_void_p, c_int64]),
@@ -122,6 +133,18 @@ SIGNATURES = {
                                         ctypes.POINTER(c_int32)]),
     "qmb_locate_window": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                          c_int32, c_int32, c_void_p, c_void_p]),
+    "qmb_locate_window_device": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                                c_int32, c_int32, ctypes.POINTER(c_void_p)]),
+    "qmb_map3d_upload": (ctypes.c_int, [c_void_p, c_dPt, c_int32, c_int32, c_int32, ctypes.POINTER(c_void_p)]),
+    "qmb_map3d_fetch": (ctypes.c_int, [c_void_p, c_dPt]),
+    "qmb_map3d_free": (ctypes.c_int, [c_void_p]),
+    "qmb_map3d_normalise": (ctypes.c_int, [c_void_p, c_void_p]),
+    "qmb_map3d_gaufilt": (ctypes.c_int, [c_void_p, c_void_p, c_double, ctypes.POINTER(c_void_p)]),
+    "qmb_map3d_peak_device": (ctypes.c_int, [c_void_p, c_void_p, ctypes.POINTER(c_int64),
+                                             ctypes.POINTER(c_double), ctypes.POINTER(c_double)]),
+    "qmb_map3d_window": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                        c_int32, c_dPt]),
+    "qmb_map3d_covfit": (ctypes.c_int, [c_void_p, c_void_p, c_dPt, c_double, c_int32, c_dPt]),
     "qmb_gaufilt3d": (ctypes.c_int, [c_void_p, c_dPt, c_int32, c_int32, c_int32, c_double, c_dPt]),
     "qmb_map3d_peak": (ctypes.c_int, [c_void_p, c_dPt, c_int64, ctypes.POINTER(c_int64),
                                       ctypes.POINTER(c_double), ctypes.POINTER(c_double)]),

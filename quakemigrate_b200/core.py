@@ -24,7 +24,7 @@ from . import _lib
 from ._lib import QmbError, c_int32, c_int64, stalta_header_t  # noqa: F401
 
 __all__ = ["migrate", "find_max_coa", "overlapping_sta_lta", "centred_sta_lta",
-           "recursive_sta_lta", "Engine", "DeviceLUT", "DeviceOnsets", "DeviceGrids", "DeviceWaveforms",
+           "recursive_sta_lta", "Engine", "DeviceLUT", "DeviceOnsets", "DeviceGrids", "DeviceWaveforms", "DeviceMap",
            "QmbError"]
 
 
@@ -181,6 +181,69 @@ class DeviceOnsets:
             pass
 
 
+class DeviceMap:
+    """
+    Handle to a float64 ``(nx, ny, nz)`` map resident on the device: the marginalised coalescence
+    map of locate() and its smoothed copy (scan.py:719-733).  Reductions and small windows come
+    back to the host; the map itself only when :meth:`fetch` is called.
+    """
+
+    def __init__(self, engine, handle, shape):
+        self.engine, self._h, self.shape = engine, handle, tuple(int(v) for v in shape)
+
+    @property
+    def nbytes(self):
+        return 8 * int(np.prod(self.shape))
+
+    def fetch(self) -> np.ndarray:
+        out = np.empty(self.shape, dtype=np.double)
+        _lib.check(_lib.load().qmb_map3d_fetch(self._h, out))
+        return out
+
+    def normalise(self) -> "DeviceMap":
+        """``map / nanmax(map)`` in place (scan.py:721)."""
+        _lib.check(_lib.load().qmb_map3d_normalise(self.engine._h, self._h))
+        return self
+
+    def peak(self):
+        """(nanargmax as ijk tuple, nanmax, nanmean) -- scan.py:869,878,972."""
+        idx, mx, mean = c_int64(-1), ctypes.c_double(0.0), ctypes.c_double(0.0)
+        _lib.check(_lib.load().qmb_map3d_peak_device(self.engine._h, self._h, ctypes.byref(idx),
+                                                     ctypes.byref(mx), ctypes.byref(mean)))
+        return tuple(int(i) for i in np.unravel_index(idx.value, self.shape)), mx.value, mean.value
+
+    def gaufilt(self, sgm: float = 0.8) -> "DeviceMap":
+        """``QuakeScan._gaufilt3d`` (scan.py:1008-1043): a new device map."""
+        h = ctypes.c_void_p()
+        _lib.check(_lib.load().qmb_map3d_gaufilt(self.engine._h, self._h, float(sgm), ctypes.byref(h)))
+        return DeviceMap(self.engine, h, self.shape)
+
+    def window(self, lo, hi) -> np.ndarray:
+        """The box ``[lo, hi)`` as a host array (the 5^3 / 7^3 fit windows, scan.py:1045-1070)."""
+        out = np.empty(tuple(int(h - l) for l, h in zip(lo, hi)), dtype=np.double)
+        _lib.check(_lib.load().qmb_map3d_window(self.engine._h, self._h, int(lo[0]), int(hi[0]), int(lo[1]),
+                                                int(hi[1]), int(lo[2]), int(hi[2]), out))
+        return out
+
+    def covfit(self, node_spacing, thresh: float = 0.90, win: int | None = None):
+        """Reductions of ``QuakeScan._covfit3d`` (scan.py:966-1001): (expectation, covariance)."""
+        sp = np.ascontiguousarray(np.broadcast_to(np.asarray(node_spacing, dtype=np.double), (3,)))
+        out = np.empty(12, dtype=np.double)
+        _lib.check(_lib.load().qmb_map3d_covfit(self.engine._h, self._h, sp, float(thresh), int(win or 0), out))
+        return out[:3].copy(), out[3:].reshape(3, 3).copy()
+
+    def free(self):
+        if self._h:
+            _lib.load().qmb_map3d_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class DeviceWaveforms:
     """Handle to a block of float64 traces ``(n_channels, n)`` resident on the device."""
 
@@ -267,6 +330,17 @@ class Engine:
         n = ctypes.c_int(0)
         _lib.check(self._lib.qmb_ctx_last_scan_bytes_per_gather(self._h, ctypes.byref(n)))
         return n.value
+
+    @property
+    def last_scan_info(self) -> dict:
+        """
+        What the last detect scan did (``qmb_scan_info_t``): operand format, the node-sum
+        verification of the 16-bit scan (windows, samples, worst relative difference, whether the
+        scan was redone with float32 rows), candidate / slow-path counts and CUDA-event times.
+        """
+        inf = _lib.ScanInfo()
+        _lib.check(self._lib.qmb_ctx_last_scan_info(self._h, ctypes.byref(inf)))
+        return {name: getattr(inf, name) for name, _ in inf._fields_ if name != "reserved"}
 
     @property
     def launch_count(self) -> int:
@@ -553,7 +627,27 @@ class Engine:
         _lib.check(self._lib.qmb_covfit3d(self._h, m, *m.shape, sp, float(thresh), int(win or 0), out))
         return out[:3].copy(), out[3:].reshape(3, 3).copy()
 
+    def upload_map(self, map3d: np.ndarray) -> DeviceMap:
+        m = np.ascontiguousarray(map3d, dtype=np.double)
+        if m.ndim != 3:
+            raise ValueError("map3d must be 3-D")
+        h = ctypes.c_void_p()
+        _lib.check(self._lib.qmb_map3d_upload(self._h, m, *m.shape, ctypes.byref(h)))
+        return DeviceMap(self, h, m.shape)
+
     # -- locate -----------------------------------------------------------------------------
+    def locate_window_device(self, lut: DeviceLUT, onsets: DeviceOnsets, fsmp: int, lsmp: int,
+                             available: int, win0: int, win1: int) -> DeviceMap:
+        """
+        :meth:`locate_window` whose result stays on the device: the un-normalised marginal map
+        ``sum_t map4d[..., win0:win1]`` (scan.py:720) as a :class:`DeviceMap`.
+        """
+        h = ctypes.c_void_p()
+        _lib.check(self._lib.qmb_locate_window_device(
+            self._h, lut._h, onsets._h, int(fsmp), int(lsmp), int(available), int(win0), int(win1),
+            ctypes.byref(h)))
+        return DeviceMap(self, h, lut.shape[:-1])
+
     def locate_window(self, lut: DeviceLUT, onsets: DeviceOnsets, fsmp: int, lsmp: int, available: int,
                       win0: int, win1: int, return_map4d: bool = False):
         """

@@ -82,6 +82,13 @@ extern "C" int qmb_ctx_last_scan_bytes_per_gather(qmb_ctx_t ctx, int *bytes) {
   return QMB_OK;
 }
 
+extern "C" int qmb_ctx_last_scan_info(qmb_ctx_t ctx, qmb_scan_info_t *info) {
+  if (!ctx || !info) QMB_FAIL(QMB_ERR_ARG, "null argument");
+  if (ctx->last_n_samples <= 0) QMB_FAIL(QMB_ERR_STATE, "no detect scan has run on this context");
+  *info = ctx->info;
+  return QMB_OK;
+}
+
 extern "C" int qmb_ctx_launch_count(qmb_ctx_t ctx, int64_t *count) {
   if (!ctx || !count) QMB_FAIL(QMB_ERR_ARG, "null argument");
   *count = ctx->launches;
@@ -125,11 +132,12 @@ extern "C" int qmb_ctx_destroy(qmb_ctx_t ctx) {
   cudaStreamSynchronize(ctx->stream);
   qmb_comm_destroy(ctx);
   ctx->pm1.release(); ctx->pm2.release(); ctx->pm3.release(); ctx->pi1.release(); ctx->pi2.release();
-  ctx->psum.release(); ctx->gm1.release(); ctx->gm2.release(); ctx->gm3.release(); ctx->gi1.release();
-  ctx->gi2.release(); ctx->gsum.release(); ctx->ex1.release(); ctx->ex2.release(); ctx->gather.release();
+  ctx->psum.release(); ctx->st_loc.release(); ctx->st_glob.release(); ctx->st_grp.release(); ctx->st_chk.release();
+  ctx->ex.release(); ctx->gather.release(); ctx->slow_flag.release(); ctx->status.release();
+  if (ctx->h_status) cudaFreeHost(ctx->h_status);
   ctx->r_max.release(); ctx->r_norm.release(); ctx->r_idx.release(); ctx->slow_list.release();
   ctx->slow_val.release(); ctx->slow_idx.release(); ctx->flush.release(); ctx->stage_lin.release();
-  ctx->q_i32.release(); ctx->q_f64.release(); ctx->pp_scratch.release(); ctx->pp_sel.release();
+  ctx->q_i32.release(); ctx->q_f64.release(); ctx->map_scratch.release(); ctx->pp_scratch.release(); ctx->pp_sel.release();
   qmb_fft_release(ctx);
   if (ctx->tmp_onsets) {
     ctx->tmp_onsets->log32.release(); ctx->tmp_onsets->log64.release(); ctx->tmp_onsets->rowmax.release();
@@ -235,6 +243,13 @@ extern "C" int qmb_comm_destroy(qmb_ctx_t ctx) {
 int qmb_nccl_allgather(qmb_ctx *ctx, const void *send, void *recv, size_t bytes_per_rank) {
   if (!ctx->nccl_comm) QMB_FAIL(QMB_ERR_STATE, "no communicator attached");
   QMB_NCCL(g_nccl.AllGather(send, recv, bytes_per_rank, ncclChar, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+  return QMB_OK;
+}
+
+int qmb_nccl_allreduce_u32(qmb_ctx *ctx, unsigned int *buf, size_t count, int take_max) {
+  if (!ctx->nccl_comm) QMB_FAIL(QMB_ERR_STATE, "no communicator attached");
+  QMB_NCCL(g_nccl.AllReduce(buf, buf, count, ncclUint32, take_max ? ncclMax : ncclMin, (ncclComm_t)ctx->nccl_comm,
+                            ctx->stream));
   return QMB_OK;
 }
 
@@ -645,4 +660,23 @@ extern "C" int qmb_locate_window(qmb_ctx_t ctx, qmb_lut_t lut, qmb_onsets_t onse
   cudaFree(d_coa);
   if (d_map) cudaFree(d_map);
   return rc;
+}
+
+// the marginal map stays on the device (locate 3-D stage works on the handle)
+extern "C" int qmb_locate_window_device(qmb_ctx_t ctx, qmb_lut_t lut, qmb_onsets_t onsets, int32_t fsmp,
+                                        int32_t lsmp, int32_t available, int32_t win0, int32_t win1,
+                                        qmb_map3d_t *coa_map) {
+  if (!ctx || !lut || !onsets || !coa_map) QMB_FAIL(QMB_ERR_ARG, "null argument");
+  *coa_map = nullptr;
+  if (lut->ctx != ctx || onsets->ctx != ctx) QMB_FAIL(QMB_ERR_ARG, "handles belong to a different context");
+  QMB_CUDA(cudaSetDevice(ctx->device));
+  qmb_map3d *m = nullptr;
+  QMB_TRY(qmb_map3d_new(ctx, lut->nxl, lut->ny, lut->nz, &m));
+  const int rc = qmb_window_run(ctx, lut, onsets, fsmp, lsmp, available, win0, win1, m->v.p, nullptr, 0);
+  if (rc != QMB_OK) {
+    qmb_map3d_free(m);
+    return rc;
+  }
+  *coa_map = m;
+  return QMB_OK;
 }

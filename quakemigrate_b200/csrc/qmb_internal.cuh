@@ -105,21 +105,28 @@ struct qmb_ctx {
   DevBuf<float> pm1, pm2, pm3;
   DevBuf<uint32_t> pi1, pi2;
   DevBuf<double> psum;
-  // merged per-sample state
-  DevBuf<float> gm1, gm2, gm3;
-  DevBuf<uint32_t> gi1, gi2;
-  DevBuf<double> gsum, ex1, ex2;
-  DevBuf<unsigned char> gather;  // all-gather staging
+  // merged per-sample state, packed [sum f64][m1 m2 m3 f32][i1 i2 u32] x Tpad (28 bytes per sample):
+  // st_loc = this rank's fold of its partials (also the all-gather send buffer), st_glob = the
+  // fold over ranks (world > 1), st_grp = the 32 group folds of the two-stage merge, st_chk = the
+  // fold of a float32 check window (node-sum verification of the 16-bit scan)
+  DevBuf<unsigned char> st_loc, st_glob, st_grp, st_chk;
+  DevBuf<double> ex;             // [2][T] float64 stacks of the two leading candidates
+  DevBuf<unsigned char> gather;  // all-gather receive staging
   // results
   DevBuf<double> r_max, r_norm;
   DevBuf<long long> r_idx;
-  DevBuf<int> slow_list;  // [0] = count, [1..] = samples
+  DevBuf<unsigned char> slow_flag;  // [T padded to 16] 1 = sample needs the all-node float64 re-scan
+  DevBuf<int> slow_list;            // [0] = listed count, [1..] = samples in ascending order
   DevBuf<double> slow_val;
   DevBuf<unsigned long long> slow_idx;
+  DevBuf<unsigned int> status;      // device-side counters of the last scan (QMB_ST_*)
+  unsigned int *h_status = nullptr; // pinned mirror
+  qmb_scan_info_t info = {};        // what the last detect scan did (qmb_ctx_last_scan_info)
   DevBuf<unsigned char> flush;  // L2 eviction scratch (benchmarks)
   DevBuf<double> stage_lin;     // H2D staging of linear onsets (reused across calls)
   DevBuf<int32_t> q_i32;        // output stage: quantised channels + unravelled indices
   DevBuf<double> q_f64;         // output stage: grid coordinates
+  DevBuf<double> map_scratch;   // locate 3-D map stage: convolution ping-pong, reductions, taps
   DevBuf<double> pp_scratch;    // pre-processing: stats, matrix powers, chunk/tile states, pass-1 output
   DevBuf<int> pp_sel;           // pre-processing: selected channel indices
   // Hilbert envelopes: cached cuFFT plan pair (handles are ints) and complex scratch
@@ -128,9 +135,11 @@ struct qmb_ctx {
   DevBuf<double> fft_buf;
   struct qmb_onsets *tmp_onsets = nullptr;  // onset rows of the one-call qmb_detect (reused)
   int32_t last_n_samples = 0;
-  // pinned staging for small D2H
-  int *h_pinned = nullptr;
 };
+
+// slots of qmb_ctx::status
+enum { QMB_ST_SLOW_TOTAL = 0, QMB_ST_TWO_CAND = 1, QMB_ST_CHECK_ERR = 2, QMB_ST_CHECK_BAD = 3,
+       QMB_ST_SLOW_LISTED = 4, QMB_ST_AGREE = 5, QMB_ST_COUNT = 8 };
 
 struct qmb_lut {
   qmb_ctx *ctx = nullptr;
@@ -172,6 +181,8 @@ struct qmb_onsets {
   DevBuf<float> log32;    // [S][stride]
   DevBuf<double> log64;   // [S][stride]
   DevBuf<double> rowmax;  // [S] max |log onset| per row (for the fp32 error bound)
+  double rowmax_sum = 0.0;  // host copy of sum(rowmax), taken when the rows are prepared
+  std::vector<double> h_rowmax;
   // 16-bit fixed-point copy for the detect scan: u = rint((x - qmin) / qstep) in [0, 65535].
   // Two streams per row over a common position axis pos = qfront + sample:
   //   stream 0 ("even"): q16[(2 s + 0) * qstride + pos] = u(sample)
@@ -181,6 +192,13 @@ struct qmb_onsets {
   DevBuf<double> qrange;  // [S][2] min / max of each row
   int64_t qstride = 0, qfront = 0;
   double qmin = 0.0, qstep = 0.0;  // qstep == 0: no quantised copy (e.g. rows of the T1 migrate())
+};
+
+struct qmb_map3d {  // float64 (nx, ny, nz) map resident on the device (locate 3-D stage)
+  qmb_ctx *ctx = nullptr;
+  int device = 0;
+  int32_t nx = 0, ny = 0, nz = 0;
+  DevBuf<double> v;
 };
 
 struct qmb_waveforms {  // device-resident float64 traces, (C, n) C-order
@@ -225,6 +243,7 @@ int qmb_onsets_combine(qmb_ctx *ctx, qmb_onsets *O, const double *d_chan, int64_
                        const int *d_row_ptr, double min_onset, double *d_lin_out);
 int qmb_nccl_allgather(qmb_ctx *ctx, const void *send, void *recv, size_t bytes_per_rank);
 int qmb_nccl_allreduce_sum_f64(qmb_ctx *ctx, double *buf, size_t count);
+int qmb_nccl_allreduce_u32(qmb_ctx *ctx, unsigned int *buf, size_t count, int take_max);
 int qmb_preprocess_device(qmb_ctx *ctx, const double *d_x, int64_t x_stride, const int *d_chan_in,
                           int32_t n_sel, int64_t n, const double *sos, int32_t nsec, int32_t detrend,
                           double taper_fraction, int32_t zerophase, int32_t decimate, double *d_out,
@@ -233,3 +252,4 @@ int qmb_envelope_device(qmb_ctx *ctx, const double *d_x, int64_t x_stride, int32
                         double *d_out, int64_t out_stride);
 void qmb_fft_release(qmb_ctx *ctx);
 qmb_ctx *qmb_default_ctx();
+int qmb_map3d_new(qmb_ctx *ctx, int32_t nx, int32_t ny, int32_t nz, qmb_map3d **out);

@@ -154,7 +154,9 @@ int gaussian_taps(int n, double sgm, std::vector<double> &w, int &m_lo, int &m_h
     const double r = m - c;
     const double v = exp(-(r * r) / (2.0 * sgm * sgm));  // util.py:110-114
     w[m] = v;
-    if (v != 0.0) {
+    // taps below 1e-22 of the central one cannot change a float64 result (the reference's FFT
+    // product is itself only good to ~1e-16 of the peak): skip them
+    if (v > 1e-22) {
       if (m < m_lo) m_lo = m;
       m_hi = m;
     }
@@ -162,20 +164,25 @@ int gaussian_taps(int n, double sgm, std::vector<double> &w, int &m_lo, int &m_h
   return QMB_OK;
 }
 
-struct MapScratch {
-  double *a = nullptr, *b = nullptr, *c = nullptr, *w = nullptr;
-  PeakPartial *part = nullptr, *peak = nullptr;
-  ~MapScratch() {
-    if (a) cudaFree(a);
-    if (b) cudaFree(b);
-    if (c) cudaFree(c);
-    if (w) cudaFree(w);
-    if (part) cudaFree(part);
-    if (peak) cudaFree(peak);
-  }
-};
-
 constexpr int RED_BLOCKS = 592;
+
+// scratch of the map stage, carved out of one context-owned buffer: [a n][b n][part][peak][cov 8*(RED+1)][taps]
+struct MapScratch {
+  double *a, *b, *cov_part, *cov_out, *taps;
+  PeakPartial *part, *peak;
+};
+int map_scratch(qmb_ctx *ctx, long long n, int n_taps, MapScratch &s) {
+  const size_t pp = (sizeof(PeakPartial) * (RED_BLOCKS + 1) + 7) / 8;
+  const size_t total = 2 * (size_t)n + pp + 8 * (RED_BLOCKS + 1) + (size_t)n_taps + 8;
+  QMB_TRY(ctx->map_scratch.ensure(total));
+  double *q = ctx->map_scratch.p;
+  s.a = q; q += n;
+  s.b = q; q += n;
+  s.part = (PeakPartial *)q; s.peak = s.part + RED_BLOCKS; q += pp;
+  s.cov_part = q; s.cov_out = q + 8 * RED_BLOCKS; q += 8 * (RED_BLOCKS + 1);
+  s.taps = q;
+  return QMB_OK;
+}
 
 int peak_of(qmb_ctx *ctx, const double *d_map, long long n, PeakPartial *d_part, PeakPartial *d_peak) {
   k_peak_partial<<<RED_BLOCKS, 256, 0, ctx->stream>>>(d_map, n, d_part);
@@ -203,67 +210,84 @@ int conv3(qmb_ctx *ctx, const double *src, double *dst, double *tmp, Dims d, con
   return QMB_OK;
 }
 
-}  // namespace
-
-// QuakeScan._gaufilt3d (scan.py:1008-1043)
-extern "C" int qmb_gaufilt3d(qmb_ctx_t ctx, const double *map3d, int32_t nx, int32_t ny, int32_t nz, double sgm,
-                             double *smoothed) {
-  if (!ctx || !map3d || !smoothed) QMB_FAIL(QMB_ERR_ARG, "null argument");
-  if (nx <= 0 || ny <= 0 || nz <= 0 || !(sgm > 0)) QMB_FAIL(QMB_ERR_ARG, "bad map shape or sigma");
-  QMB_CUDA(cudaSetDevice(ctx->device));
-  const Dims d = {nx, ny, nz};
-  const long long n = (long long)nx * ny * nz;
-  MapScratch s;
-  QMB_CUDA(cudaMalloc((void **)&s.a, n * sizeof(double)));
-  QMB_CUDA(cudaMalloc((void **)&s.b, n * sizeof(double)));
-  QMB_CUDA(cudaMalloc((void **)&s.part, RED_BLOCKS * sizeof(PeakPartial)));
-  QMB_CUDA(cudaMalloc((void **)&s.peak, sizeof(PeakPartial)));
-  std::vector<double> w, wa;
-  int lo[3], hi[3], off[3];
-  const int ns[3] = {nx, ny, nz};
-  for (int a = 0; a < 3; ++a) {
-    gaussian_taps(ns[a], sgm, w, lo[a], hi[a]);
-    off[a] = (int)wa.size();
-    wa.insert(wa.end(), w.begin(), w.end());
-  }
-  QMB_CUDA(cudaMalloc((void **)&s.w, wa.size() * sizeof(double)));
-  QMB_CUDA(cudaMemcpyAsync(s.w, wa.data(), wa.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  QMB_CUDA(cudaMemcpyAsync(s.a, map3d, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  const int blocks = (int)((n + 255) / 256);
-  QMB_CUDA(cudaMalloc((void **)&s.c, n * sizeof(double)));
-  double *tmp = s.c;
-  int rc = QMB_OK;
-  for (int rep = 0; rep < 2 && rc == QMB_OK; ++rep) {
-    // a -> (conv) -> b ; b -> (mirror, / max) -> a
-    rc = conv3(ctx, s.a, s.b, tmp, d, s.w, lo, hi, off);
-    if (rc == QMB_OK) rc = peak_of(ctx, s.b, n, s.part, s.peak);
-    if (rc == QMB_OK) {
-      k_mirror_scale<<<blocks, 256, 0, ctx->stream>>>(s.b, s.a, n, s.peak);
-      ctx->launches++;
-    }
-  }
-  cudaError_t e = cudaGetLastError();
-  if (rc == QMB_OK && e == cudaSuccess)
-    e = cudaMemcpyAsync(smoothed, s.a, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  if (rc == QMB_OK && e != cudaSuccess) {
-    qmb_set_error("qmb_gaufilt3d: %s", cudaGetErrorString(e));
-    rc = QMB_ERR_CUDA;
-  }
-  return rc;
+__global__ void __launch_bounds__(256) k_scale_by_peak(double *map, long long n, const PeakPartial *peak) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) map[i] = map[i] / peak->mx;
 }
 
-// nanargmax (first), nanmax, nanmean of a map (scan.py:869,878,972)
-extern "C" int qmb_map3d_peak(qmb_ctx_t ctx, const double *map3d, int64_t n, int64_t *argmax, double *maxval,
-                              double *mean) {
-  if (!ctx || !map3d || n <= 0) QMB_FAIL(QMB_ERR_ARG, "bad argument");
+// copy the box [lo, hi) of a map into a dense (hi-lo) C-order block
+__global__ void k_map_window(const double *map, Dims d, int x0, int y0, int z0, int wx, int wy, int wz, double *out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= wx * wy * wz) return;
+  const int iz = i % wz, iy = (i / wz) % wy, ix = i / (wz * wy);
+  out[i] = map[((long long)(x0 + ix) * d.ny + (y0 + iy)) * d.nz + (z0 + iz)];
+}
+
+int check_map(qmb_ctx *ctx, qmb_map3d *m) {
+  if (!ctx || !m) QMB_FAIL(QMB_ERR_ARG, "null argument");
+  if (m->ctx != ctx) QMB_FAIL(QMB_ERR_ARG, "map belongs to a different context");
   QMB_CUDA(cudaSetDevice(ctx->device));
+  return QMB_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// device-resident maps
+// ---------------------------------------------------------------------------------------------
+int qmb_map3d_new(qmb_ctx *ctx, int32_t nx, int32_t ny, int32_t nz, qmb_map3d **out) {
+  *out = nullptr;
+  if (nx <= 0 || ny <= 0 || nz <= 0) QMB_FAIL(QMB_ERR_ARG, "bad map shape");
+  qmb_map3d *m = new qmb_map3d();
+  m->ctx = ctx; m->device = ctx->device; m->nx = nx; m->ny = ny; m->nz = nz;
+  const int rc = m->v.ensure((size_t)nx * ny * nz);
+  if (rc != QMB_OK) {
+    delete m;
+    return rc;
+  }
+  *out = m;
+  return QMB_OK;
+}
+
+extern "C" int qmb_map3d_upload(qmb_ctx_t ctx, const double *map3d, int32_t nx, int32_t ny, int32_t nz,
+                                qmb_map3d_t *out) {
+  if (!ctx || !map3d || !out) QMB_FAIL(QMB_ERR_ARG, "null argument");
+  QMB_CUDA(cudaSetDevice(ctx->device));
+  qmb_map3d *m = nullptr;
+  QMB_TRY(qmb_map3d_new(ctx, nx, ny, nz, &m));
+  cudaError_t e = cudaMemcpyAsync(m->v.p, map3d, m->v.bytes(), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    qmb_map3d_free(m);
+    QMB_FAIL(QMB_ERR_CUDA, "qmb_map3d_upload: %s", cudaGetErrorString(e));
+  }
+  *out = m;
+  return QMB_OK;
+}
+
+extern "C" int qmb_map3d_fetch(qmb_map3d_t m, double *host) {
+  if (!m || !host) QMB_FAIL(QMB_ERR_ARG, "null argument");
+  QMB_CUDA(cudaSetDevice(m->device));
+  QMB_CUDA(cudaMemcpyAsync(host, m->v.p, m->v.bytes(), cudaMemcpyDeviceToHost, m->ctx->stream));
+  QMB_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  return QMB_OK;
+}
+
+extern "C" int qmb_map3d_free(qmb_map3d_t m) {
+  if (!m) return QMB_OK;
+  cudaSetDevice(m->device);
+  m->v.release();
+  delete m;
+  return QMB_OK;
+}
+
+// nanargmax (first, C order), nanmax, nanmean (scan.py:869,878,972); 32 bytes come back
+extern "C" int qmb_map3d_peak_device(qmb_ctx_t ctx, qmb_map3d_t m, int64_t *argmax, double *maxval, double *mean) {
+  QMB_TRY(check_map(ctx, m));
+  const long long n = (long long)m->nx * m->ny * m->nz;
   MapScratch s;
-  QMB_CUDA(cudaMalloc((void **)&s.a, n * sizeof(double)));
-  QMB_CUDA(cudaMalloc((void **)&s.part, RED_BLOCKS * sizeof(PeakPartial)));
-  QMB_CUDA(cudaMalloc((void **)&s.peak, sizeof(PeakPartial)));
-  QMB_CUDA(cudaMemcpyAsync(s.a, map3d, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  QMB_TRY(peak_of(ctx, s.a, n, s.part, s.peak));
+  QMB_TRY(map_scratch(ctx, 0, 0, s));
+  QMB_TRY(peak_of(ctx, m->v.p, n, s.part, s.peak));
   PeakPartial h;
   QMB_CUDA(cudaMemcpyAsync(&h, s.peak, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
   QMB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -273,28 +297,103 @@ extern "C" int qmb_map3d_peak(qmb_ctx_t ctx, const double *map3d, int64_t n, int
   return QMB_OK;
 }
 
+// map / nanmax(map) in place (scan.py:721)
+extern "C" int qmb_map3d_normalise(qmb_ctx_t ctx, qmb_map3d_t m) {
+  QMB_TRY(check_map(ctx, m));
+  const long long n = (long long)m->nx * m->ny * m->nz;
+  MapScratch s;
+  QMB_TRY(map_scratch(ctx, 0, 0, s));
+  QMB_TRY(peak_of(ctx, m->v.p, n, s.part, s.peak));
+  k_scale_by_peak<<<(int)((n + 255) / 256), 256, 0, ctx->stream>>>(m->v.p, n, s.peak);
+  ctx->launches++;
+  QMB_CUDA(cudaGetLastError());
+  return QMB_OK;
+}
+
+// QuakeScan._gaufilt3d (scan.py:1008-1043): new device map
+extern "C" int qmb_map3d_gaufilt(qmb_ctx_t ctx, qmb_map3d_t m, double sgm, qmb_map3d_t *out) {
+  QMB_TRY(check_map(ctx, m));
+  if (!out) QMB_FAIL(QMB_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (!(sgm > 0)) QMB_FAIL(QMB_ERR_ARG, "bad sigma");
+  const Dims d = {m->nx, m->ny, m->nz};
+  const long long n = (long long)d.nx * d.ny * d.nz;
+  std::vector<double> w, wa;
+  int lo[3], hi[3], off[3];
+  const int ns[3] = {d.nx, d.ny, d.nz};
+  for (int a = 0; a < 3; ++a) {
+    gaussian_taps(ns[a], sgm, w, lo[a], hi[a]);
+    off[a] = (int)wa.size();
+    wa.insert(wa.end(), w.begin(), w.end());
+  }
+  MapScratch s;
+  QMB_TRY(map_scratch(ctx, n, (int)wa.size(), s));
+  qmb_map3d *r = nullptr;
+  QMB_TRY(qmb_map3d_new(ctx, d.nx, d.ny, d.nz, &r));
+  // the taps are consumed by kernels of this stream only; a pageable H2D copy returns after the
+  // source has been staged, so `wa` may go out of scope
+  cudaError_t e = cudaMemcpyAsync(s.taps, wa.data(), wa.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  int rc = e == cudaSuccess ? QMB_OK : QMB_ERR_CUDA;
+  if (rc != QMB_OK) qmb_set_error("qmb_map3d_gaufilt: %s", cudaGetErrorString(e));
+  const int blocks = (int)((n + 255) / 256);
+  const double *src = m->v.p;
+  for (int rep = 0; rep < 2 && rc == QMB_OK; ++rep) {
+    // src -> (conv) -> a ; a -> (mirror, / max) -> r
+    rc = conv3(ctx, src, s.a, s.b, d, s.taps, lo, hi, off);
+    if (rc == QMB_OK) rc = peak_of(ctx, s.a, n, s.part, s.peak);
+    if (rc == QMB_OK) {
+      k_mirror_scale<<<blocks, 256, 0, ctx->stream>>>(s.a, r->v.p, n, s.peak);
+      ctx->launches++;
+    }
+    src = r->v.p;
+  }
+  if (rc == QMB_OK && cudaGetLastError() != cudaSuccess) {
+    qmb_set_error("qmb_map3d_gaufilt: kernel launch failed");
+    rc = QMB_ERR_CUDA;
+  }
+  if (rc != QMB_OK) {
+    qmb_map3d_free(r);
+    return rc;
+  }
+  *out = r;
+  return QMB_OK;
+}
+
+// box [x0,x1) x [y0,y1) x [z0,z1) of a map to the host, C order (the 5^3 / 7^3 fit windows)
+extern "C" int qmb_map3d_window(qmb_ctx_t ctx, qmb_map3d_t m, int32_t x0, int32_t x1, int32_t y0, int32_t y1,
+                                int32_t z0, int32_t z1, double *host) {
+  QMB_TRY(check_map(ctx, m));
+  if (!host) QMB_FAIL(QMB_ERR_ARG, "null argument");
+  if (x0 < 0 || y0 < 0 || z0 < 0 || x1 > m->nx || y1 > m->ny || z1 > m->nz || x0 >= x1 || y0 >= y1 || z0 >= z1)
+    QMB_FAIL(QMB_ERR_ARG, "window outside the map");
+  const long long cnt = (long long)(x1 - x0) * (y1 - y0) * (z1 - z0);
+  if (cnt > (1 << 20)) QMB_FAIL(QMB_ERR_ARG, "window too large (use qmb_map3d_fetch)");
+  MapScratch s;
+  QMB_TRY(map_scratch(ctx, cnt, 0, s));
+  const Dims d = {m->nx, m->ny, m->nz};
+  k_map_window<<<(int)((cnt + 127) / 128), 128, 0, ctx->stream>>>(m->v.p, d, x0, y0, z0, x1 - x0, y1 - y0, z1 - z0, s.a);
+  ctx->launches++;
+  QMB_CUDA(cudaGetLastError());
+  QMB_CUDA(cudaMemcpyAsync(host, s.a, cnt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  QMB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return QMB_OK;
+}
+
 // reductions of QuakeScan._covfit3d (scan.py:939-1005).  out[0..2] = expectation (xe, ye, ze) in
 // grid units * spacing (relative to the grid origin), out[3..11] = 3x3 covariance matrix (row major).
 // win <= 0: whole grid; else nodes within +-(win-1)//2 of the maximum (scan.py:1045-1070).
-extern "C" int qmb_covfit3d(qmb_ctx_t ctx, const double *map3d, int32_t nx, int32_t ny, int32_t nz,
-                            const double *spacing, double thresh, int32_t win, double *out12) {
-  if (!ctx || !map3d || !spacing || !out12) QMB_FAIL(QMB_ERR_ARG, "null argument");
-  if (nx <= 0 || ny <= 0 || nz <= 0) QMB_FAIL(QMB_ERR_ARG, "bad map shape");
-  QMB_CUDA(cudaSetDevice(ctx->device));
+extern "C" int qmb_map3d_covfit(qmb_ctx_t ctx, qmb_map3d_t m, const double *spacing, double thresh, int32_t win,
+                                double *out12) {
+  QMB_TRY(check_map(ctx, m));
+  if (!spacing || !out12) QMB_FAIL(QMB_ERR_ARG, "null argument");
+  const int nx = m->nx, ny = m->ny, nz = m->nz;
   const long long n = (long long)nx * ny * nz;
   MapScratch s;
-  double *d_part = nullptr, *d_out = nullptr;
-  QMB_CUDA(cudaMalloc((void **)&s.a, n * sizeof(double)));
-  QMB_CUDA(cudaMalloc((void **)&s.b, (RED_BLOCKS * 8 + 8) * sizeof(double)));
-  QMB_CUDA(cudaMalloc((void **)&s.part, RED_BLOCKS * sizeof(PeakPartial)));
-  QMB_CUDA(cudaMalloc((void **)&s.peak, sizeof(PeakPartial)));
-  d_part = s.b;
-  d_out = s.b + RED_BLOCKS * 8;
-  QMB_CUDA(cudaMemcpyAsync(s.a, map3d, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  QMB_TRY(map_scratch(ctx, 0, 0, s));
   CovParams p = {};
-  p.map = s.a; p.d = {nx, ny, nz}; p.sx = spacing[0]; p.sy = spacing[1]; p.sz = spacing[2]; p.thresh = thresh;
+  p.map = m->v.p; p.d = {nx, ny, nz}; p.sx = spacing[0]; p.sy = spacing[1]; p.sz = spacing[2]; p.thresh = thresh;
   if (win > 0) {
-    QMB_TRY(peak_of(ctx, s.a, n, s.part, s.peak));
+    QMB_TRY(peak_of(ctx, m->v.p, n, s.part, s.peak));
     PeakPartial h;
     QMB_CUDA(cudaMemcpyAsync(&h, s.peak, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     QMB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -308,19 +407,19 @@ extern "C" int qmb_covfit3d(qmb_ctx_t ctx, const double *map3d, int32_t nx, int3
     p.z1 = clip(iz - w2, nz); p.z2 = clip(iz + w2 + 1, nz);
   }
   double h1[8], h2[8];
-  k_cov_partial<1><<<RED_BLOCKS, 256, 0, ctx->stream>>>(p, d_part);
-  k_cov_final<<<1, 1, 0, ctx->stream>>>(d_part, RED_BLOCKS, d_out);
+  k_cov_partial<1><<<RED_BLOCKS, 256, 0, ctx->stream>>>(p, s.cov_part);
+  k_cov_final<<<1, 1, 0, ctx->stream>>>(s.cov_part, RED_BLOCKS, s.cov_out);
   ctx->launches += 2;
   QMB_CUDA(cudaGetLastError());
-  QMB_CUDA(cudaMemcpyAsync(h1, d_out, 7 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  QMB_CUDA(cudaMemcpyAsync(h1, s.cov_out, 7 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   QMB_CUDA(cudaStreamSynchronize(ctx->stream));
   const double ssw = h1[0];
   p.xe = h1[1] / ssw; p.ye = h1[2] / ssw; p.ze = h1[3] / ssw;
-  k_cov_partial<2><<<RED_BLOCKS, 256, 0, ctx->stream>>>(p, d_part);
-  k_cov_final<<<1, 1, 0, ctx->stream>>>(d_part, RED_BLOCKS, d_out);
+  k_cov_partial<2><<<RED_BLOCKS, 256, 0, ctx->stream>>>(p, s.cov_part);
+  k_cov_final<<<1, 1, 0, ctx->stream>>>(s.cov_part, RED_BLOCKS, s.cov_out);
   ctx->launches += 2;
   QMB_CUDA(cudaGetLastError());
-  QMB_CUDA(cudaMemcpyAsync(h2, d_out, 7 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  QMB_CUDA(cudaMemcpyAsync(h2, s.cov_out, 7 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   QMB_CUDA(cudaStreamSynchronize(ctx->stream));
   out12[0] = p.xe; out12[1] = p.ye; out12[2] = p.ze;
   const double cxx = h2[0] / ssw, cyy = h2[1] / ssw, czz = h2[2] / ssw, cxy = h2[3] / ssw, cxz = h2[4] / ssw,
@@ -328,6 +427,43 @@ extern "C" int qmb_covfit3d(qmb_ctx_t ctx, const double *map3d, int32_t nx, int3
   const double cov[9] = {cxx, cxy, cxz, cxy, cyy, cyz, cxz, cyz, czz};
   for (int k = 0; k < 9; ++k) out12[3 + k] = cov[k];
   return QMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer forms (upload -> device form -> fetch)
+// ---------------------------------------------------------------------------------------------
+extern "C" int qmb_gaufilt3d(qmb_ctx_t ctx, const double *map3d, int32_t nx, int32_t ny, int32_t nz, double sgm,
+                             double *smoothed) {
+  if (!ctx || !map3d || !smoothed) QMB_FAIL(QMB_ERR_ARG, "null argument");
+  if (nx <= 0 || ny <= 0 || nz <= 0 || !(sgm > 0)) QMB_FAIL(QMB_ERR_ARG, "bad map shape or sigma");
+  qmb_map3d_t m = nullptr, r = nullptr;
+  QMB_TRY(qmb_map3d_upload(ctx, map3d, nx, ny, nz, &m));
+  int rc = qmb_map3d_gaufilt(ctx, m, sgm, &r);
+  if (rc == QMB_OK) rc = qmb_map3d_fetch(r, smoothed);
+  qmb_map3d_free(m);
+  qmb_map3d_free(r);
+  return rc;
+}
+
+extern "C" int qmb_map3d_peak(qmb_ctx_t ctx, const double *map3d, int64_t n, int64_t *argmax, double *maxval,
+                              double *mean) {
+  if (!ctx || !map3d || n <= 0 || n > 0x7fffffffLL) QMB_FAIL(QMB_ERR_ARG, "bad argument");
+  qmb_map3d_t m = nullptr;
+  QMB_TRY(qmb_map3d_upload(ctx, map3d, 1, 1, (int32_t)n, &m));
+  const int rc = qmb_map3d_peak_device(ctx, m, argmax, maxval, mean);
+  qmb_map3d_free(m);
+  return rc;
+}
+
+extern "C" int qmb_covfit3d(qmb_ctx_t ctx, const double *map3d, int32_t nx, int32_t ny, int32_t nz,
+                            const double *spacing, double thresh, int32_t win, double *out12) {
+  if (!ctx || !map3d || !spacing || !out12) QMB_FAIL(QMB_ERR_ARG, "null argument");
+  if (nx <= 0 || ny <= 0 || nz <= 0) QMB_FAIL(QMB_ERR_ARG, "bad map shape");
+  qmb_map3d_t m = nullptr;
+  QMB_TRY(qmb_map3d_upload(ctx, map3d, nx, ny, nz, &m));
+  const int rc = qmb_map3d_covfit(ctx, m, spacing, thresh, win, out12);
+  qmb_map3d_free(m);
+  return rc;
 }
 
 // ---------------------------------------------------------------------------------------------

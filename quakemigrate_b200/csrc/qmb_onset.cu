@@ -277,6 +277,20 @@ __global__ void __launch_bounds__(256) k_onset_quantise(const double *log64, lon
 // Build the 16-bit streams of O (after its float64 rows exist).  One common grid for all rows:
 // qmin = the smallest value present (so that the clip floor, the most frequent value of real
 // onsets, is represented exactly), qstep = (max - min) / 65535.
+// host copy of sum_rows max|log onset| (the float32 error bound of the scan needs it per call;
+// taking it here keeps the scan itself free of host round trips)
+static int onsets_rowmax_to_host(qmb_ctx *ctx, qmb_onsets *O, bool sync) {
+  O->h_rowmax.resize((size_t)O->S);
+  QMB_CUDA(cudaMemcpyAsync(O->h_rowmax.data(), O->rowmax.p, O->S * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (sync) QMB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return QMB_OK;
+}
+static void onsets_rowmax_sum(qmb_onsets *O) {
+  double a = 0.0;
+  for (double v : O->h_rowmax) a += v;
+  O->rowmax_sum = a;
+}
+
 int qmb_onsets_quantise(qmb_ctx *ctx, qmb_onsets *O) {
   O->qstep = 0.0;
   if (O->S <= 0 || O->P <= 0) return QMB_OK;
@@ -285,8 +299,10 @@ int qmb_onsets_quantise(qmb_ctx *ctx, qmb_onsets *O) {
   ctx->launches++;
   QMB_CUDA(cudaGetLastError());
   std::vector<double> range((size_t)2 * O->S);
+  QMB_TRY(onsets_rowmax_to_host(ctx, O, false));
   QMB_CUDA(cudaMemcpyAsync(range.data(), O->qrange.p, range.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   QMB_CUDA(cudaStreamSynchronize(ctx->stream));
+  onsets_rowmax_sum(O);
   double mn = range[0], mx = range[1];
   for (int s = 0; s < O->S; ++s) {
     if (range[2 * s] < mn) mn = range[2 * s];
@@ -377,6 +393,8 @@ int qmb_onsets_prepare(qmb_ctx *ctx, qmb_onsets *O, const double *d_linear, int 
   QMB_CUDA(cudaGetLastError());
   if (already_log) {  // rows of the reference-compatible migrate(): float32 window pass only
     O->qstep = 0.0;
+    QMB_TRY(onsets_rowmax_to_host(ctx, O, true));
+    onsets_rowmax_sum(O);
     return QMB_OK;
   }
   return qmb_onsets_quantise(ctx, O);

@@ -35,6 +35,7 @@
 #include <math.h>
 
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -500,8 +501,25 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// top-3 bookkeeping shared by the merge kernels
+// merged per-sample state: packed [sum f64][m1 m2 m3 f32][i1 i2 u32], each array Tp long
 // ---------------------------------------------------------------------------------------------
+struct MState {
+  double *sum;
+  float *m1, *m2, *m3;
+  uint32_t *i1, *i2;
+};
+constexpr size_t MSTATE_BYTES = 28;  // per sample
+__host__ __device__ inline MState mstate(unsigned char *b, size_t Tp) {
+  MState s;
+  s.sum = (double *)b;
+  s.m1 = (float *)(b + Tp * 8);
+  s.m2 = (float *)(b + Tp * 12);
+  s.m3 = (float *)(b + Tp * 16);
+  s.i1 = (uint32_t *)(b + Tp * 20);
+  s.i2 = (uint32_t *)(b + Tp * 24);
+  return s;
+}
+
 struct Top3 {
   float m1, m2, m3;
   uint32_t i1, i2;
@@ -515,13 +533,13 @@ __device__ __forceinline__ void top3_insert(Top3 &a, float v, uint32_t i) {
   a.i1 = g1 ? i : a.i1;
 }
 
-// merge `n_parts` partial reductions per sample: part q lives at [q * stride + t]
+// merge `n_parts` partial reductions per sample: part q lives at [q * stride + t] (float / uint32
+// arrays) and [q * stride_sum + t] (sums).  blockIdx.y selects a group of parts; group g writes
+// its fold into the packed state at out + g * Tp * 28 bytes (two-stage merge).
 __global__ void __launch_bounds__(256) k_merge(const float *pm1, const float *pm2, const float *pm3,
                                                const uint32_t *pi1, const uint32_t *pi2,
                                                const double *psum, int n_parts, long long stride,
-                                               long long stride_sum, long long n, float *gm1, float *gm2, float *gm3,
-                                               uint32_t *gi1, uint32_t *gi2, double *gsum) {
-  // blockIdx.y selects a group of parts; group g writes its fold at offset g * n (two-stage merge)
+                                               long long stride_sum, long long n, unsigned char *out) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   const int per = (n_parts + gridDim.y - 1) / gridDim.y;
@@ -537,10 +555,10 @@ __global__ void __launch_bounds__(256) k_merge(const float *pm1, const float *pm
     a.m3 = fmaxf(a.m3, pm3[o]);
     s += psum[(size_t)q * stride_sum + t];
   }
-  const size_t w = (size_t)blockIdx.y * n + t;
-  gm1[w] = a.m1; gm2[w] = a.m2; gm3[w] = a.m3;
-  gi1[w] = a.i1; gi2[w] = a.i2;
-  gsum[w] = s;
+  const MState g = mstate(out + (size_t)blockIdx.y * (size_t)n * MSTATE_BYTES, (size_t)n);
+  g.m1[t] = a.m1; g.m2[t] = a.m2; g.m3[t] = a.m3;
+  g.i1[t] = a.i1; g.i2[t] = a.i2;
+  g.sum[t] = s;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -570,141 +588,217 @@ __device__ double exact_stack(const ExactParams &e, long long gnode, long long t
   return acc;
 }
 
-// ex1/ex2[t'] = float64 stack of candidate 1 / 2 when owned by this rank, else 0 (summed across
+// ex1/ex2[t] = float64 stack of candidate 1 / 2 when owned by this rank, else 0 (summed across
 // ranks afterwards).  Candidate 2 is only evaluated when it can matter.
-__global__ void __launch_bounds__(128) k_exact(ExactParams e, const float *gm1, const float *gm2,
-                                               const uint32_t *gi1, const uint32_t *gi2, float thr,
-                                               int shift, long long n_samples, double *ex1, double *ex2) {
+__global__ void __launch_bounds__(128) k_exact(ExactParams e, MState g, float thr, int shift, long long n_samples,
+                                               double *ex1, double *ex2) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // output sample
   if (t >= n_samples) return;
   const long long tp = t + shift;
   double a = 0.0, b = 0.0;
-  const long long c1 = gi1[tp], c2 = gi2[tp];
+  const long long c1 = g.i1[tp], c2 = g.i2[tp];
   if (c1 != 0xFFFFFFFFLL && c1 >= e.node_offset && c1 < e.node_offset + e.n_local) a = exact_stack(e, c1, t);
-  if (gm1[tp] - gm2[tp] <= thr && c2 != 0xFFFFFFFFLL && c2 >= e.node_offset &&
+  if (g.m1[tp] - g.m2[tp] <= thr && c2 != 0xFFFFFFFFLL && c2 >= e.node_offset &&
       c2 < e.node_offset + e.n_local)
     b = exact_stack(e, c2, t);
   ex1[t] = a;
   ex2[t] = b;
 }
 
-// decide winner per sample; queue samples that need the all-node float64 re-scan
-__global__ void __launch_bounds__(256) k_finalize(const float *gm1, const float *gm2, const float *gm3,
-                                                  const uint32_t *gi1, const uint32_t *gi2,
-                                                  const double *gsum, const double *ex1, const double *ex2,
-                                                  float thr, int shift, long long n_samples, double avail,
-                                                  double n_nodes_global, double *r_max, double *r_norm,
-                                                  long long *r_idx, int *slow_list, int slow_cap) {
+// decide the winner per sample; FLAG samples that need the all-node float64 re-scan (three or
+// more candidates inside the band).  The flags are compacted in sample order by k_slow_compact,
+// so the queue is identical on every rank and in every run without a host sort.
+__global__ void __launch_bounds__(256) k_finalize(MState g, const double *ex1, const double *ex2, float thr, int shift,
+                                                  long long n_samples, double avail, double n_nodes_global,
+                                                  double *r_max, double *r_norm, long long *r_idx,
+                                                  unsigned char *slow_flag, unsigned int *status) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_samples) return;
-  const long long tp = t + shift;
-  const float a1 = gm1[tp], a2 = gm2[tp], a3 = gm3[tp];
-  double best = exp(ex1[t] / avail);
-  long long idx = gi1[tp];
-  if (a1 - a2 <= thr) {
-    const double other = exp(ex2[t] / avail);
-    const long long oi = gi2[tp];
-    if (oi != 0xFFFFFFFFLL && (other > best || (other == best && oi < idx))) {
-      best = other;
-      idx = oi;
+  bool two = false;
+  if (t < n_samples) {
+    const long long tp = t + shift;
+    const float a1 = g.m1[tp], a2 = g.m2[tp], a3 = g.m3[tp];
+    double best = exp(ex1[t] / avail);
+    long long idx = g.i1[tp];
+    bool slow = false;
+    if (a1 - a2 <= thr) {
+      two = true;
+      const double other = exp(ex2[t] / avail);
+      const long long oi = g.i2[tp];
+      if (oi != 0xFFFFFFFFLL && (other > best || (other == best && oi < idx))) {
+        best = other;
+        idx = oi;
+      }
+      slow = a1 - a3 <= thr;
     }
-    if (a1 - a3 <= thr) {  // three or more candidates: full float64 re-scan of this sample
-      const int slot = atomicAdd(&slow_list[0], 1);
-      if (slot < slow_cap) slow_list[1 + slot] = (int)t;
-    }
+    slow_flag[t] = slow ? 1 : 0;
+    r_max[t] = best;
+    r_idx[t] = idx;
+    r_norm[t] = best * n_nodes_global / g.sum[tp];
   }
-  r_max[t] = best;
-  r_idx[t] = idx;
-  r_norm[t] = best * n_nodes_global / gsum[tp];
+  const unsigned m = __ballot_sync(0xffffffffu, two);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(&status[QMB_ST_TWO_CAND], (unsigned)__popc(m));
+}
+
+// Ordered compaction of the slow-path flags (one CTA): the samples of rank [skip, skip + cap) in
+// ascending order go to slow_list[1..], their number to slow_list[0] and status[SLOW_LISTED], the
+// number of flagged samples to status[SLOW_TOTAL].  `flag` is zero-padded to a multiple of 16.
+__global__ void __launch_bounds__(1024) k_slow_compact(const unsigned char *flag, long long n, int skip, int cap,
+                                                       int *slow_list, unsigned int *status) {
+  __shared__ int wsum[32];
+  __shared__ int total_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long chunk = (((n + 1023) / 1024) + 15) & ~15LL;
+  const long long b0 = (long long)tid * chunk, b1 = min(n, b0 + chunk);
+  int cnt = 0;
+  for (long long i = b0; i < b1; i += 16) {
+    const uint4 w = *reinterpret_cast<const uint4 *>(flag + i);
+    cnt += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+  }
+  int incl = cnt;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = wsum[lane], wi = w;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += v;
+    }
+    wsum[lane] = wi - w;  // exclusive
+    if (lane == 31) total_s = wi;
+  }
+  __syncthreads();
+  int r = wsum[warp] + incl - cnt;
+  if (cnt) {
+    for (long long i = b0; i < b1; ++i)
+      if (flag[i]) {
+        if (r >= skip && r < skip + cap) slow_list[1 + r - skip] = (int)i;
+        ++r;
+      }
+  }
+  if (tid == 0) {
+    const int total = total_s;
+    int listed = total - skip;
+    listed = listed < 0 ? 0 : (listed > cap ? cap : listed);
+    slow_list[0] = listed;
+    status[QMB_ST_SLOW_TOTAL] = (unsigned)total;
+    status[QMB_ST_SLOW_LISTED] = (unsigned)listed;
+  }
 }
 
 // slow path: for each queued sample, float64 coalescence of every local node; per-CTA best
-// (value, lowest index) written to partial arrays [cta][slot].
+// (value, lowest index) written to partial arrays [cta][slot].  Persistent: the queue length is
+// read from the device, batches of SLOW_BATCH samples are walked inside the kernel.
 constexpr int SLOW_BATCH = 8;
-__global__ void __launch_bounds__(128) k_slow(ExactParams e, const int *slow_list, int n_slow, int batch_offset,
-                                              double avail, const uint32_t *nodeidx, int n_tiles,
-                                              double *part_val, unsigned long long *part_idx) {
-  // grid.x = CTAs striding over tiles, grid.y = batch of SLOW_BATCH queued samples
-  const int b0 = (blockIdx.y + batch_offset) * SLOW_BATCH;
-  const int nb = min(SLOW_BATCH, n_slow - b0);
-  long long ts[SLOW_BATCH];
-  for (int b = 0; b < SLOW_BATCH; ++b) ts[b] = (b < nb) ? slow_list[1 + b0 + b] : 0;
-  double best[SLOW_BATCH];
-  unsigned long long bidx[SLOW_BATCH];
-  for (int b = 0; b < SLOW_BATCH; ++b) { best[b] = -1.0; bidx[b] = ~0ull; }
-  const int slots_per_cta = blockDim.x;  // one thread per node slot, several tiles per pass
-  const int tiles_per_pass = slots_per_cta / e.NB > 0 ? slots_per_cta / e.NB : 1;
-  for (int j0 = blockIdx.x * tiles_per_pass; j0 < n_tiles; j0 += gridDim.x * tiles_per_pass) {
-    const int j = j0 + threadIdx.x / e.NB, q = threadIdx.x % e.NB;
-    if (j >= n_tiles || (int)threadIdx.x >= tiles_per_pass * e.NB) continue;
-    const uint32_t gi = nodeidx[(size_t)j * e.NB + q];
-    if (gi == 0xFFFFFFFFu) continue;
-    double acc[SLOW_BATCH];
-    for (int b = 0; b < SLOW_BATCH; ++b) acc[b] = 0.0;
-    for (int s = 0; s < e.S; ++s) {
-      const size_t m = (size_t)j * e.Spad + s;
-      const long long tau = (long long)e.tmin[m] + e.tau16[m * e.NB + q];
-      const double *row = e.on64 + (size_t)s * e.row_stride + e.origin + tau;
-#pragma unroll
-      for (int b = 0; b < SLOW_BATCH; ++b) acc[b] += row[ts[b]];
-    }
-#pragma unroll
-    for (int b = 0; b < SLOW_BATCH; ++b) {
-      const double c = exp(acc[b] / avail);
-      if (c > best[b] || (c == best[b] && (unsigned long long)gi < bidx[b])) { best[b] = c; bidx[b] = gi; }
-    }
-  }
-  // block reduce (value desc, index asc)
+constexpr int SLOW_CAP = 4096;  // queued samples handled per round (more: further rounds)
+__global__ void __launch_bounds__(128) k_slow(ExactParams e, const int *slow_list, int cap, double avail,
+                                              const uint32_t *nodeidx, int n_tiles, double *part_val,
+                                              unsigned long long *part_idx) {
+  const int n_slow = slow_list[0];
   __shared__ double sv[128];
   __shared__ unsigned long long si[128];
-  for (int b = 0; b < nb; ++b) {
-    sv[threadIdx.x] = best[b];
-    si[threadIdx.x] = bidx[b];
-    __syncthreads();
-    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-      if ((int)threadIdx.x < o) {
-        const double v = sv[threadIdx.x + o];
-        const unsigned long long i = si[threadIdx.x + o];
-        if (v > sv[threadIdx.x] || (v == sv[threadIdx.x] && i < si[threadIdx.x])) {
-          sv[threadIdx.x] = v;
-          si[threadIdx.x] = i;
+  const int slots_per_cta = blockDim.x;  // one thread per node slot, several tiles per pass
+  const int tiles_per_pass = slots_per_cta / e.NB > 0 ? slots_per_cta / e.NB : 1;
+  for (int b0 = 0; b0 < n_slow; b0 += SLOW_BATCH) {
+    const int nb = min(SLOW_BATCH, n_slow - b0);
+    long long ts[SLOW_BATCH];
+    for (int b = 0; b < SLOW_BATCH; ++b) ts[b] = (b < nb) ? slow_list[1 + b0 + b] : 0;
+    double best[SLOW_BATCH];
+    unsigned long long bidx[SLOW_BATCH];
+    for (int b = 0; b < SLOW_BATCH; ++b) { best[b] = -1.0; bidx[b] = ~0ull; }
+    for (int j0 = blockIdx.x * tiles_per_pass; j0 < n_tiles; j0 += gridDim.x * tiles_per_pass) {
+      const int j = j0 + threadIdx.x / e.NB, q = threadIdx.x % e.NB;
+      if (j >= n_tiles || (int)threadIdx.x >= tiles_per_pass * e.NB) continue;
+      const uint32_t gi = nodeidx[(size_t)j * e.NB + q];
+      if (gi == 0xFFFFFFFFu) continue;
+      double acc[SLOW_BATCH];
+      for (int b = 0; b < SLOW_BATCH; ++b) acc[b] = 0.0;
+      for (int s = 0; s < e.S; ++s) {
+        const size_t m = (size_t)j * e.Spad + s;
+        const long long tau = (long long)e.tmin[m] + e.tau16[m * e.NB + q];
+        const double *row = e.on64 + (size_t)s * e.row_stride + e.origin + tau;
+#pragma unroll
+        for (int b = 0; b < SLOW_BATCH; ++b) acc[b] += row[ts[b]];
+      }
+#pragma unroll
+      for (int b = 0; b < SLOW_BATCH; ++b) {
+        const double c = exp(acc[b] / avail);
+        if (c > best[b] || (c == best[b] && (unsigned long long)gi < bidx[b])) { best[b] = c; bidx[b] = gi; }
+      }
+    }
+    // block reduce (value desc, index asc)
+    for (int b = 0; b < nb; ++b) {
+      sv[threadIdx.x] = best[b];
+      si[threadIdx.x] = bidx[b];
+      __syncthreads();
+      for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+          const double v = sv[threadIdx.x + o];
+          const unsigned long long i = si[threadIdx.x + o];
+          if (v > sv[threadIdx.x] || (v == sv[threadIdx.x] && i < si[threadIdx.x])) {
+            sv[threadIdx.x] = v;
+            si[threadIdx.x] = i;
+          }
         }
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) {
+        part_val[(size_t)blockIdx.x * cap + b0 + b] = sv[0];
+        part_idx[(size_t)blockIdx.x * cap + b0 + b] = si[0];
       }
       __syncthreads();
     }
-    if (threadIdx.x == 0) {
-      part_val[(size_t)blockIdx.x * n_slow + b0 + b] = sv[0];
-      part_idx[(size_t)blockIdx.x * n_slow + b0 + b] = si[0];
-    }
-    __syncthreads();
   }
 }
 
-// fold [n_parts][n_slow] partials; optionally scatter into the result arrays
-__global__ void k_slow_merge(const double *part_val, const unsigned long long *part_idx, int n_parts,
-                             int n_slow, double *out_val, unsigned long long *out_idx) {
+// fold [n_parts][cap] partials of the listed samples (count read from the device)
+__global__ void k_slow_merge(const double *part_val, const unsigned long long *part_idx, int n_parts, int cap,
+                             const int *slow_list, double *out_val, unsigned long long *out_idx) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= n_slow) return;
+  if (b >= slow_list[0]) return;
   double best = -1.0;
   unsigned long long bi = ~0ull;
   for (int q = 0; q < n_parts; ++q) {
-    const double v = part_val[(size_t)q * n_slow + b];
-    const unsigned long long i = part_idx[(size_t)q * n_slow + b];
+    const double v = part_val[(size_t)q * cap + b];
+    const unsigned long long i = part_idx[(size_t)q * cap + b];
     if (v > best || (v == best && i < bi)) { best = v; bi = i; }
   }
   out_val[b] = best;
   out_idx[b] = bi;
 }
 
-__global__ void k_slow_scatter(const int *slow_list, int n_slow, const double *val,
-                               const unsigned long long *idx, const double *gsum, int shift,
-                               double n_nodes_global, double *r_max, double *r_norm, long long *r_idx) {
+__global__ void k_slow_scatter(const int *slow_list, const double *val, const unsigned long long *idx,
+                               const double *gsum, int shift, double n_nodes_global, double *r_max,
+                               double *r_norm, long long *r_idx) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= n_slow) return;
+  if (b >= slow_list[0]) return;
   const int t = slow_list[1 + b];
   r_max[t] = val[b];
   r_idx[t] = (long long)idx[b];
   r_norm[t] = val[b] * n_nodes_global / gsum[t + shift];
+}
+
+// node-sum verification of the 16-bit scan: worst relative difference between the sums of the
+// 16-bit scan (q_sum, this rank's nodes) and of a float32 re-scan of the same samples (f_sum)
+__global__ void __launch_bounds__(256) k_check_sum(const double *f_sum, const double *q_sum, int n,
+                                                   unsigned int *status) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  float rel = 0.f;
+  if (t < n) {
+    const double f = f_sum[t], q = q_sum[t];
+    rel = (float)(fabs(q - f) / f);
+    if (!(rel >= 0.f)) rel = __int_as_float(0x7fc00000);  // NaN orders above everything as bits
+  }
+  unsigned bits = __float_as_uint(rel);
+  for (int o = 16; o > 0; o >>= 1) bits = max(bits, __shfl_xor_sync(0xffffffffu, bits, o));
+  if ((threadIdx.x & 31) == 0 && bits) atomicMax(&status[QMB_ST_CHECK_ERR], bits);
+}
+__global__ void k_check_decide(unsigned int *status, float tol) {
+  const float e = __uint_as_float(status[QMB_ST_CHECK_ERR]);
+  status[QMB_ST_CHECK_BAD] = (e <= tol) ? 0u : 1u;
 }
 
 template <int W, int NPW, int K, int MODE, int CR>
@@ -765,7 +859,8 @@ int dispatch_scan_q16(qmb_ctx *ctx, const QmbVariant &v, const ScanParams &p, in
 // ---------------------------------------------------------------------------------------------
 // Tiling decisions shared by the detect scan and the window pass.
 static int scan_setup(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, long long first, long long T,
-                      int32_t available, ScanParams &p, size_t &smem, int &shift_out, bool use_q = false) {
+                      int32_t available, ScanParams &p, size_t &smem, int &shift_out, bool use_q = false,
+                      int items_per_sm = 32) {
   const int K = L->v.K, TT = 32 * K, NB = L->NB;
   p.on32 = O->log32.p;
   p.row_stride = O->stride;
@@ -810,7 +905,7 @@ static int scan_setup(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, long long first, 
   // pick the R in [R0, 4 R0] that minimises it (>= 8 tiles per item, partial buffers <= 3 GiB).
   const int grid = ctx->sm_count;
   const int W = L->v.W;
-  int R0 = (32 * grid + p.n_time_tiles - 1) / p.n_time_tiles;
+  int R0 = (items_per_sm * grid + p.n_time_tiles - 1) / p.n_time_tiles;
   if (R0 < 1) R0 = 1;
   int maxR = L->n_tiles / 8;
   if (maxR < 1) maxR = 1;
@@ -871,54 +966,103 @@ int qmb_window_run(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, int32_t fsmp, int32_
   return dispatch_scan<1>(ctx, L->v, p, ctx->sm_count, smem);
 }
 
-int qmb_scan_run(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, int32_t fsmp, int32_t lsmp,
-                 int32_t available, float *kernel_ms) {
+
+// ---------------------------------------------------------------------------------------------
+// detect: scan -> merge -> (exchange) -> float64 candidates -> decision -> slow path -> check
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct CheckWindow {
+  ScanParams p;
+  size_t smem;
+  int shift;
+  long long w0, len;
+};
+
+constexpr long long CHECK_LEN = 248;   // one time tile of the float32 kernel whatever the alignment shift
+constexpr float CHECK_TOL = 2e-6f;     // node-sum difference above which the 16-bit result is discarded
+
+int scan_run_impl(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, int32_t fsmp, int32_t lsmp, int32_t available,
+                  float *kernel_ms, bool force_fp32, float earlier_ms) {
   long long T;
   QMB_TRY(check_scan_args(L, O, fsmp, lsmp, available, T));
   ScanParams p = {};
   size_t smem;
   int shift;
   // detect scans read 16-bit fixed-point rows unless float32 was asked for (or the table / rows
-  // have no 16-bit form); candidates are re-evaluated in float64 either way
-  bool use_q = ctx->scan_fp32 != 1 && O->qstep > 0.0 && O->q16.p && L->RSq > 0 && L->tauq16.p &&
+  // have no 16-bit form); candidates are re-evaluated in float64 either way.  The automatic mode
+  // keeps float32 rows for short scans (the verification windows would cost more than they save)
+  // and verifies the node sums of every 16-bit scan (see CheckWindow).
+  bool use_q = !force_fp32 && ctx->scan_fp32 != 1 && O->qstep > 0.0 && O->q16.p && L->RSq > 0 && L->tauq16.p &&
                q16_variant(L->v) && O->S <= 256;  // sum(u) < 2^24: exact in float32
-  if (use_q && ctx->scan_fp32 == 0) {
-    // automatic choice: the 16-bit rows leave arg-max and max_coa exact, but max_norm_coa divides
-    // by a node sum built from the quantised stacks.  One node's coalescence is off by about
-    // sigma = qstep * sqrt(S / 12) / available (relative), and the sum over N nodes averages that
-    // down by ~sqrt(N) (less where neighbouring nodes share samples: a factor 32 is held back).
-    // Keep float32 rows when that estimate is not clearly inside the 1e-5 bar (tiny grids, or
-    // `available` much smaller than the number of rows).
-    const double sigma = O->qstep * sqrt((double)O->S / 12.0) / (double)available;
-    if (32.0 * sigma / sqrt((double)L->n_global) > 5e-6) use_q = false;
-  }
+  if (use_q && ctx->scan_fp32 == 0 && T < 2048) use_q = false;
   if (use_q && scan_setup(ctx, L, O, fsmp, T, available, p, smem, shift, true) != QMB_OK) {
     use_q = false;  // e.g. too few pipeline stages for the (slightly wider) 16-bit rows
     p = ScanParams{};
   }
+  QMB_TRY(ctx->status.ensure(QMB_ST_COUNT));
+  if (!ctx->h_status) QMB_CUDA(cudaHostAlloc((void **)&ctx->h_status, QMB_ST_COUNT * sizeof(unsigned int), cudaHostAllocDefault));
+  if (ctx->world > 1 && !force_fp32) {
+    // the operand format fixes the candidate threshold, and every rank must fold the exchanged
+    // state identically: 16-bit rows only when every rank can use them
+    ctx->h_status[QMB_ST_AGREE] = use_q ? 1u : 0u;
+    QMB_CUDA(cudaMemcpyAsync(ctx->status.p + QMB_ST_AGREE, ctx->h_status + QMB_ST_AGREE, sizeof(unsigned int),
+                             cudaMemcpyHostToDevice, ctx->stream));
+    QMB_TRY(qmb_nccl_allreduce_u32(ctx, ctx->status.p + QMB_ST_AGREE, 1, 0));
+    QMB_CUDA(cudaMemcpyAsync(ctx->h_status + QMB_ST_AGREE, ctx->status.p + QMB_ST_AGREE, sizeof(unsigned int),
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    QMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (use_q && ctx->h_status[QMB_ST_AGREE] == 0u) {
+      use_q = false;
+      p = ScanParams{};
+    }
+  }
   if (!use_q) QMB_TRY(scan_setup(ctx, L, O, fsmp, T, available, p, smem, shift, false));
-  const int R = p.R, grid = ctx->sm_count;
+  const int R = p.R, grid = ctx->sm_count, W = L->v.W;
 
-  const size_t n_part = (size_t)R * L->v.W * p.Tpad;
+  // ---- verification windows of the 16-bit scan (float32 re-scan of a few time tiles) -----------
+  CheckWindow chk[2];
+  int n_chk = 0;
+  size_t n_part_chk = 0, tp_chk = 0;
+  if (use_q) {
+    n_chk = T >= 16384 ? 2 : 1;
+    for (int c = 0; c < n_chk; ++c) {
+      CheckWindow &cw = chk[c];
+      cw.len = std::min<long long>(CHECK_LEN, T);
+      cw.w0 = ((2LL * c + 1) * T) / (2LL * n_chk) - cw.len / 2;
+      cw.w0 = std::max<long long>(0, std::min<long long>(cw.w0, T - cw.len));
+      cw.p = ScanParams{};
+      QMB_TRY(scan_setup(ctx, L, O, (long long)fsmp + cw.w0, cw.len, available, cw.p, cw.smem, cw.shift, false, 4));
+      n_part_chk = std::max(n_part_chk, (size_t)cw.p.R * W * (size_t)cw.p.Tpad);
+      tp_chk = std::max(tp_chk, (size_t)cw.p.Tpad);
+    }
+  }
+
+  const size_t n_part = std::max<size_t>((size_t)R * W * (size_t)p.Tpad, n_part_chk);
   QMB_TRY(ctx->pm1.ensure(n_part)); QMB_TRY(ctx->pm2.ensure(n_part)); QMB_TRY(ctx->pm3.ensure(n_part));
   QMB_TRY(ctx->pi1.ensure(n_part)); QMB_TRY(ctx->pi2.ensure(n_part)); QMB_TRY(ctx->psum.ensure(n_part));
   p.pm1 = ctx->pm1.p; p.pm2 = ctx->pm2.p; p.pm3 = ctx->pm3.p;
   p.pi1 = ctx->pi1.p; p.pi2 = ctx->pi2.p; p.psum = ctx->psum.p;
   const size_t Tp = (size_t)p.Tpad;
-  QMB_TRY(ctx->gm1.ensure(Tp * 33)); QMB_TRY(ctx->gm2.ensure(Tp * 33)); QMB_TRY(ctx->gm3.ensure(Tp * 33));
-  QMB_TRY(ctx->gi1.ensure(Tp * 33)); QMB_TRY(ctx->gi2.ensure(Tp * 33)); QMB_TRY(ctx->gsum.ensure(Tp * 33));
-  QMB_TRY(ctx->ex1.ensure(Tp)); QMB_TRY(ctx->ex2.ensure(Tp));
+  constexpr int GROUPS = 32;
+  QMB_TRY(ctx->st_loc.ensure(Tp * MSTATE_BYTES));
+  QMB_TRY(ctx->st_grp.ensure(std::max(Tp, tp_chk) * MSTATE_BYTES * GROUPS));
+  if (ctx->world > 1) {
+    QMB_TRY(ctx->st_glob.ensure(Tp * MSTATE_BYTES));
+    QMB_TRY(ctx->gather.ensure(std::max(Tp * MSTATE_BYTES, (size_t)SLOW_CAP * 16) * (size_t)ctx->world));
+  }
+  if (n_chk) QMB_TRY(ctx->st_chk.ensure(tp_chk * MSTATE_BYTES));
+  QMB_TRY(ctx->ex.ensure(2 * (size_t)T));
   QMB_TRY(ctx->r_max.ensure((size_t)T)); QMB_TRY(ctx->r_norm.ensure((size_t)T)); QMB_TRY(ctx->r_idx.ensure((size_t)T));
-  const int slow_cap = (int)T;
-  QMB_TRY(ctx->slow_list.ensure((size_t)slow_cap + 1));
+  const size_t flag_bytes = (((size_t)T + 15) & ~(size_t)15) + 16;
+  QMB_TRY(ctx->slow_flag.ensure(flag_bytes));
+  QMB_TRY(ctx->slow_list.ensure((size_t)SLOW_CAP + 1));
+  const int slow_ctas = 4 * ctx->sm_count;
+  QMB_TRY(ctx->slow_val.ensure((size_t)(slow_ctas + 1) * SLOW_CAP));
+  QMB_TRY(ctx->slow_idx.ensure((size_t)(slow_ctas + 1) * SLOW_CAP));
 
   // fp32 error bound (see file header): delta = S * 2^-24 * sum_rows max|v|, threshold 2*delta
-  std::vector<double> rowmax(O->S);
-  QMB_CUDA(cudaMemcpyAsync(rowmax.data(), O->rowmax.p, O->S * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  QMB_CUDA(cudaStreamSynchronize(ctx->stream));
-  double A = 0.0;
-  for (double v : rowmax) A += v;
-  float thr = (float)(2.0 * 1.001 * (double)O->S * 5.9604644775390625e-08 * A) + 1e-30f;
+  float thr = (float)(2.0 * 1.001 * (double)O->S * 5.9604644775390625e-08 * O->rowmax_sum) + 1e-30f;
   if (use_q) {
     // |quantised stack - exact| <= S * qstep / 2 (rounding to the grid) + the float32 evaluation of
     // qc0 + qstep * sum(u): rounding of qstep, of qc0 and of the fma, each <= 2^-24 of
@@ -929,58 +1073,46 @@ int qmb_scan_run(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, int32_t fsmp, int32_t 
   }
   ctx->last_scan_q16 = use_q ? 1 : 0;
 
+  QMB_CUDA(cudaMemsetAsync(ctx->status.p, 0, QMB_ST_COUNT * sizeof(unsigned int), ctx->stream));
+  QMB_CUDA(cudaMemsetAsync(ctx->slow_flag.p, 0, flag_bytes, ctx->stream));
   QMB_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-  int rc;
-  rc = use_q ? dispatch_scan_q16(ctx, L->v, p, grid, smem) : dispatch_scan<0>(ctx, L->v, p, grid, smem);
-  QMB_TRY(rc);
+  QMB_TRY(use_q ? dispatch_scan_q16(ctx, L->v, p, grid, smem) : dispatch_scan<0>(ctx, L->v, p, grid, smem));
   QMB_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
 
   // ---- merge partials (local), then across ranks ----------------------------------------------
-  const int mb = (int)((p.Tpad + 255) / 256);
-  {
-    // many parts (short scans over big grids): fold in G groups first, then fold the groups.
-    // The group results live behind the final arrays (offset Tpad).
-    const int n_parts = R * L->v.W;
-    const int G = n_parts >= 256 ? 32 : 1;
-    if (G > 1) {
-      k_merge<<<dim3(mb, G), 256, 0, ctx->stream>>>(p.pm1, p.pm2, p.pm3, p.pi1, p.pi2, p.psum, n_parts, p.Tpad,
-                                                    p.Tpad, p.Tpad, ctx->gm1.p + Tp, ctx->gm2.p + Tp,
-                                                    ctx->gm3.p + Tp, ctx->gi1.p + Tp, ctx->gi2.p + Tp,
-                                                    ctx->gsum.p + Tp);
-      k_merge<<<mb, 256, 0, ctx->stream>>>(ctx->gm1.p + Tp, ctx->gm2.p + Tp, ctx->gm3.p + Tp, ctx->gi1.p + Tp,
-                                           ctx->gi2.p + Tp, ctx->gsum.p + Tp, G, p.Tpad, p.Tpad, p.Tpad,
-                                           ctx->gm1.p, ctx->gm2.p, ctx->gm3.p, ctx->gi1.p, ctx->gi2.p, ctx->gsum.p);
-      ctx->launches++;
+  // many parts (short scans over big grids): fold in GROUPS groups first, then fold the groups
+  auto merge_parts = [&](const ScanParams &sp, unsigned char *out) -> int {
+    const int n_parts = sp.R * W;
+    const long long tp = sp.Tpad;
+    const int mb = (int)((tp + 255) / 256);
+    if (n_parts >= 256) {
+      k_merge<<<dim3(mb, GROUPS), 256, 0, ctx->stream>>>(sp.pm1, sp.pm2, sp.pm3, sp.pi1, sp.pi2, sp.psum, n_parts,
+                                                         tp, tp, tp, ctx->st_grp.p);
+      const MState g = mstate(ctx->st_grp.p, (size_t)tp);
+      k_merge<<<mb, 256, 0, ctx->stream>>>(g.m1, g.m2, g.m3, g.i1, g.i2, g.sum, GROUPS, tp * 7, (tp * 7) / 2, tp, out);
+      ctx->launches += 2;
     } else {
-      k_merge<<<mb, 256, 0, ctx->stream>>>(p.pm1, p.pm2, p.pm3, p.pi1, p.pi2, p.psum, n_parts, p.Tpad, p.Tpad,
-                                           p.Tpad, ctx->gm1.p, ctx->gm2.p, ctx->gm3.p, ctx->gi1.p, ctx->gi2.p,
-                                           ctx->gsum.p);
+      k_merge<<<mb, 256, 0, ctx->stream>>>(sp.pm1, sp.pm2, sp.pm3, sp.pi1, sp.pi2, sp.psum, n_parts, tp, tp, tp, out);
+      ctx->launches++;
     }
-  }
-  ctx->launches++;
-  QMB_CUDA(cudaGetLastError());
+    QMB_CUDA(cudaGetLastError());
+    return QMB_OK;
+  };
+  QMB_TRY(merge_parts(p, ctx->st_loc.p));
+  unsigned char *glob = ctx->st_loc.p;
+  const int mb = (int)((p.Tpad + 255) / 256);
   if (ctx->world > 1) {
-    // pack the six arrays contiguously, all-gather, merge again
-    const size_t per = Tp * (3 * sizeof(float) + 2 * sizeof(uint32_t) + sizeof(double));
-    QMB_TRY(ctx->gather.ensure(per * (size_t)(ctx->world + 1)));
-    unsigned char *send = ctx->gather.p, *recv = ctx->gather.p + per;
-    size_t o = 0;
-    QMB_CUDA(cudaMemcpyAsync(send + o, ctx->gsum.p, Tp * 8, cudaMemcpyDeviceToDevice, ctx->stream)); o += Tp * 8;
-    QMB_CUDA(cudaMemcpyAsync(send + o, ctx->gm1.p, Tp * 4, cudaMemcpyDeviceToDevice, ctx->stream)); o += Tp * 4;
-    QMB_CUDA(cudaMemcpyAsync(send + o, ctx->gm2.p, Tp * 4, cudaMemcpyDeviceToDevice, ctx->stream)); o += Tp * 4;
-    QMB_CUDA(cudaMemcpyAsync(send + o, ctx->gm3.p, Tp * 4, cudaMemcpyDeviceToDevice, ctx->stream)); o += Tp * 4;
-    QMB_CUDA(cudaMemcpyAsync(send + o, ctx->gi1.p, Tp * 4, cudaMemcpyDeviceToDevice, ctx->stream)); o += Tp * 4;
-    QMB_CUDA(cudaMemcpyAsync(send + o, ctx->gi2.p, Tp * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-    QMB_TRY(qmb_nccl_allgather(ctx, send, recv, per));
-    const long long stride_f = (long long)(per / 4), stride_d = (long long)(per / 8);
-    k_merge<<<mb, 256, 0, ctx->stream>>>((const float *)(recv + Tp * 8), (const float *)(recv + Tp * 12),
-                                         (const float *)(recv + Tp * 16), (const uint32_t *)(recv + Tp * 20),
-                                         (const uint32_t *)(recv + Tp * 24), (const double *)recv, ctx->world,
-                                         stride_f, stride_d, p.Tpad, ctx->gm1.p, ctx->gm2.p, ctx->gm3.p, ctx->gi1.p,
-                                         ctx->gi2.p, ctx->gsum.p);
+    // the packed local state is the send buffer: all-gather, fold the ranks identically everywhere
+    const size_t per = Tp * MSTATE_BYTES;
+    QMB_TRY(qmb_nccl_allgather(ctx, ctx->st_loc.p, ctx->gather.p, per));
+    const MState g = mstate(ctx->gather.p, Tp);
+    k_merge<<<mb, 256, 0, ctx->stream>>>(g.m1, g.m2, g.m3, g.i1, g.i2, g.sum, ctx->world, (long long)(per / 4),
+                                         (long long)(per / 8), p.Tpad, ctx->st_glob.p);
     ctx->launches++;
     QMB_CUDA(cudaGetLastError());
+    glob = ctx->st_glob.p;
   }
+  const MState G = mstate(glob, Tp);
 
   // ---- float64 re-evaluation of the candidates + decision -------------------------------------
   ExactParams e = {};
@@ -988,82 +1120,128 @@ int qmb_scan_run(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, int32_t fsmp, int32_t 
   e.S = L->S; e.Spad = L->Spad; e.tau16 = L->tau16.p; e.tmin = L->tmin.p;
   e.slotmap = L->slotmap.p; e.NB = L->NB;
   e.node_offset = L->node_offset; e.n_local = L->n_local;
-  k_exact<<<(int)((T + 127) / 128), 128, 0, ctx->stream>>>(e, ctx->gm1.p, ctx->gm2.p, ctx->gi1.p, ctx->gi2.p,
-                                                            thr, shift, T, ctx->ex1.p, ctx->ex2.p);
+  double *ex1 = ctx->ex.p, *ex2 = ctx->ex.p + T;
+  k_exact<<<(int)((T + 127) / 128), 128, 0, ctx->stream>>>(e, G, thr, shift, T, ex1, ex2);
   ctx->launches++;
   QMB_CUDA(cudaGetLastError());
-  if (ctx->world > 1) {
-    QMB_TRY(qmb_nccl_allreduce_sum_f64(ctx, ctx->ex1.p, (size_t)T));
-    QMB_TRY(qmb_nccl_allreduce_sum_f64(ctx, ctx->ex2.p, (size_t)T));
-  }
-  QMB_CUDA(cudaMemsetAsync(ctx->slow_list.p, 0, sizeof(int), ctx->stream));
-  k_finalize<<<(int)((T + 255) / 256), 256, 0, ctx->stream>>>(
-      ctx->gm1.p, ctx->gm2.p, ctx->gm3.p, ctx->gi1.p, ctx->gi2.p, ctx->gsum.p, ctx->ex1.p, ctx->ex2.p, thr,
-      shift, T, (double)available, (double)L->n_global, ctx->r_max.p, ctx->r_norm.p, ctx->r_idx.p,
-      ctx->slow_list.p, slow_cap);
+  if (ctx->world > 1) QMB_TRY(qmb_nccl_allreduce_sum_f64(ctx, ctx->ex.p, 2 * (size_t)T));  // one owner per candidate
+  k_finalize<<<(int)((T + 255) / 256), 256, 0, ctx->stream>>>(G, ex1, ex2, thr, shift, T, (double)available,
+                                                              (double)L->n_global, ctx->r_max.p, ctx->r_norm.p,
+                                                              ctx->r_idx.p, ctx->slow_flag.p, ctx->status.p);
   ctx->launches++;
   QMB_CUDA(cudaGetLastError());
 
-  // ---- slow path (needs the queue length on the host) ------------------------------------------
-  int n_slow = 0;
-  QMB_CUDA(cudaMemcpyAsync(&n_slow, ctx->slow_list.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  QMB_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (n_slow > slow_cap) n_slow = slow_cap;
-  if (n_slow > 0) {
-    // the queue was filled with atomics: put it in ascending sample order so that every rank
-    // (and every run) walks it identically -- the cross-rank fold pairs entries by position
-    std::vector<int> q((size_t)n_slow);
-    QMB_CUDA(cudaMemcpyAsync(q.data(), ctx->slow_list.p + 1, (size_t)n_slow * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    QMB_CUDA(cudaStreamSynchronize(ctx->stream));
-    std::sort(q.begin(), q.end());
-    QMB_CUDA(cudaMemcpyAsync(ctx->slow_list.p + 1, q.data(), (size_t)n_slow * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    QMB_CUDA(cudaStreamSynchronize(ctx->stream));
-    const int ctas = 4 * ctx->sm_count;
-    const int n_batches = (n_slow + SLOW_BATCH - 1) / SLOW_BATCH;
-    const size_t per_rank = (size_t)n_slow;
-    QMB_TRY(ctx->slow_val.ensure((size_t)(ctas + ctx->world + 1) * per_rank));
-    QMB_TRY(ctx->slow_idx.ensure((size_t)(ctas + ctx->world + 1) * per_rank));
-    double *pv = ctx->slow_val.p;
-    unsigned long long *pi = ctx->slow_idx.p;
-    double *mv = pv + (size_t)ctas * per_rank;             // merged (local)  [n_slow]
-    unsigned long long *mi = pi + (size_t)ctas * per_rank;
-    // chunk batches over grid.y (<= 65535)
-    for (int b0 = 0; b0 < n_batches; b0 += 32768) {
-      const int nb = (n_batches - b0 < 32768) ? n_batches - b0 : 32768;
-      k_slow<<<dim3(ctas, nb), 128, 0, ctx->stream>>>(e, ctx->slow_list.p, n_slow, b0, (double)available,
-                                                      L->nodeidx.p, L->n_tiles, pv, pi);
-      ctx->launches++;
-      QMB_CUDA(cudaGetLastError());
-    }
-    k_slow_merge<<<(n_slow + 127) / 128, 128, 0, ctx->stream>>>(pv, pi, ctas, n_slow, mv, mi);
-    ctx->launches++;
+  // ---- slow path, driven from the device: no host round trip ------------------------------------
+  double *pv = ctx->slow_val.p, *mv = pv + (size_t)slow_ctas * SLOW_CAP;
+  unsigned long long *pi = ctx->slow_idx.p, *mi = pi + (size_t)slow_ctas * SLOW_CAP;
+  auto slow_round = [&](int skip) -> int {
+    k_slow_compact<<<1, 1024, 0, ctx->stream>>>(ctx->slow_flag.p, T, skip, SLOW_CAP, ctx->slow_list.p, ctx->status.p);
+    k_slow<<<slow_ctas, 128, 0, ctx->stream>>>(e, ctx->slow_list.p, SLOW_CAP, (double)available, L->nodeidx.p,
+                                               L->n_tiles, pv, pi);
+    k_slow_merge<<<SLOW_CAP / 128, 128, 0, ctx->stream>>>(pv, pi, slow_ctas, SLOW_CAP, ctx->slow_list.p, mv, mi);
+    ctx->launches += 3;
     QMB_CUDA(cudaGetLastError());
     if (ctx->world > 1) {
-      // gather every rank's (value, index) per queued sample and fold again
-      QMB_TRY(ctx->gather.ensure((size_t)(ctx->world) * per_rank * 16 + 16));
-      double *gv = (double *)ctx->gather.p;
-      unsigned long long *gi = (unsigned long long *)(ctx->gather.p + (size_t)ctx->world * per_rank * 8);
-      QMB_TRY(qmb_nccl_allgather(ctx, mv, gv, per_rank * 8));
-      QMB_TRY(qmb_nccl_allgather(ctx, mi, gi, per_rank * 8));
-      k_slow_merge<<<(n_slow + 127) / 128, 128, 0, ctx->stream>>>(gv, gi, ctx->world, n_slow, mv, mi);
+      // every rank lists the same samples (identical merged state): exchange a fixed-size block
+      // [values | indices] per rank and fold again
+      unsigned char *send = ctx->st_grp.p;  // scratch, free at this point
+      QMB_CUDA(cudaMemcpyAsync(send, mv, (size_t)SLOW_CAP * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+      QMB_CUDA(cudaMemcpyAsync(send + (size_t)SLOW_CAP * 8, mi, (size_t)SLOW_CAP * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+      QMB_TRY(qmb_nccl_allgather(ctx, send, ctx->gather.p, (size_t)SLOW_CAP * 16));
+      // rank r: values at gather + r * CAP * 16, indices CAP * 8 bytes further: a "part" stride of 2 * CAP
+      k_slow_merge<<<SLOW_CAP / 128, 128, 0, ctx->stream>>>((const double *)ctx->gather.p,
+                                                            (const unsigned long long *)(ctx->gather.p + (size_t)SLOW_CAP * 8),
+                                                            ctx->world, 2 * SLOW_CAP, ctx->slow_list.p, mv, mi);
       ctx->launches++;
       QMB_CUDA(cudaGetLastError());
     }
-    k_slow_scatter<<<(n_slow + 127) / 128, 128, 0, ctx->stream>>>(ctx->slow_list.p, n_slow, mv, mi, ctx->gsum.p,
-                                                                  shift, (double)L->n_global, ctx->r_max.p,
-                                                                  ctx->r_norm.p, ctx->r_idx.p);
+    k_slow_scatter<<<SLOW_CAP / 128, 128, 0, ctx->stream>>>(ctx->slow_list.p, mv, mi, G.sum, shift, (double)L->n_global,
+                                                            ctx->r_max.p, ctx->r_norm.p, ctx->r_idx.p);
+    ctx->launches++;
+    QMB_CUDA(cudaGetLastError());
+    return QMB_OK;
+  };
+  QMB_TRY(slow_round(0));
+
+  // ---- node-sum verification of the 16-bit scan ---------------------------------------------------
+  QMB_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
+  int chk_samples = 0;
+  for (int c = 0; c < n_chk; ++c) {
+    CheckWindow &cw = chk[c];
+    cw.p.pm1 = ctx->pm1.p; cw.p.pm2 = ctx->pm2.p; cw.p.pm3 = ctx->pm3.p;
+    cw.p.pi1 = ctx->pi1.p; cw.p.pi2 = ctx->pi2.p; cw.p.psum = ctx->psum.p;
+    QMB_TRY(dispatch_scan<0>(ctx, L->v, cw.p, grid, cw.smem));
+    QMB_TRY(merge_parts(cw.p, ctx->st_chk.p));
+    const MState F = mstate(ctx->st_chk.p, (size_t)cw.p.Tpad), Q = mstate(ctx->st_loc.p, Tp);
+    k_check_sum<<<(int)((cw.len + 255) / 256), 256, 0, ctx->stream>>>(F.sum + cw.shift, Q.sum + shift + cw.w0,
+                                                                      (int)cw.len, ctx->status.p);
+    ctx->launches++;
+    QMB_CUDA(cudaGetLastError());
+    chk_samples += (int)cw.len;
+  }
+  if (n_chk) {
+    if (ctx->world > 1) QMB_TRY(qmb_nccl_allreduce_u32(ctx, ctx->status.p + QMB_ST_CHECK_ERR, 1, 1));
+    k_check_decide<<<1, 1, 0, ctx->stream>>>(ctx->status.p, CHECK_TOL);
     ctx->launches++;
     QMB_CUDA(cudaGetLastError());
   }
   QMB_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+  QMB_CUDA(cudaMemcpyAsync(ctx->h_status, ctx->status.p, QMB_ST_COUNT * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
   QMB_CUDA(cudaStreamSynchronize(ctx->stream));
+
+  float ms_scan = 0.f, ms_tail = 0.f, ms_total = 0.f, ms_check = 0.f;
+  cudaEventElapsedTime(&ms_scan, ctx->ev[0], ctx->ev[1]);
+  cudaEventElapsedTime(&ms_tail, ctx->ev[1], ctx->ev[2]);
+  cudaEventElapsedTime(&ms_total, ctx->ev[0], ctx->ev[2]);
+  cudaEventElapsedTime(&ms_check, ctx->ev[3], ctx->ev[2]);
+  const int n_slow = (int)ctx->h_status[QMB_ST_SLOW_TOTAL];
+  int syncs = 0;
+
+  const bool bad = n_chk && ctx->h_status[QMB_ST_CHECK_BAD] != 0u;
+  float check_err = 0.f;
+  memcpy(&check_err, &ctx->h_status[QMB_ST_CHECK_ERR], sizeof(float));
+  if (bad && ctx->scan_fp32 == 0) {
+    // the quantised node sums are not trustworthy on this input: redo the scan with float32 rows
+    QMB_TRY(scan_run_impl(ctx, L, O, fsmp, lsmp, available, kernel_ms, true, earlier_ms + ms_total));
+    ctx->info.fell_back_fp32 = 1;
+    ctx->info.check_windows = n_chk;
+    ctx->info.check_samples = chk_samples;
+    ctx->info.check_max_rel_err = (double)check_err;
+    ctx->info.check_ms = ms_check;
+    ctx->info.host_syncs_in_timed_region += 1;
+    return QMB_OK;
+  }
+
+  if (n_slow > SLOW_CAP) {
+    // more queued samples than one round holds (pathological, e.g. all-tied data): further rounds
+    for (int skip = SLOW_CAP; skip < n_slow; skip += SLOW_CAP) QMB_TRY(slow_round(skip));
+    QMB_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+    QMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ms_tail, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ms_total, ctx->ev[0], ctx->ev[2]);
+    syncs = 1;
+  }
   ctx->last_n_samples = (int32_t)T;
+  qmb_scan_info_t &inf = ctx->info;
+  inf = qmb_scan_info_t{};
+  inf.operand_bytes = use_q ? 2 : 4;
+  inf.fell_back_fp32 = 0;
+  inf.check_windows = n_chk;
+  inf.check_samples = chk_samples;
+  inf.check_max_rel_err = n_chk ? (double)check_err : 0.0;
+  inf.slow_path_samples = n_slow;
+  inf.two_candidate_samples = (int)ctx->h_status[QMB_ST_TWO_CAND];
+  inf.scan_ms = ms_scan; inf.tail_ms = ms_tail; inf.total_ms = ms_total + earlier_ms; inf.check_ms = ms_check;
+  inf.host_syncs_in_timed_region = syncs;
   if (kernel_ms) {
-    float a = 0.f, b = 0.f, c = 0.f;
-    cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
-    cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]);
-    cudaEventElapsedTime(&c, ctx->ev[0], ctx->ev[2]);
-    kernel_ms[0] = a; kernel_ms[1] = b; kernel_ms[2] = c; kernel_ms[3] = (float)n_slow;
+    kernel_ms[0] = ms_scan; kernel_ms[1] = ms_tail; kernel_ms[2] = ms_total + earlier_ms; kernel_ms[3] = (float)n_slow;
   }
   return QMB_OK;
+}
+
+}  // namespace
+
+int qmb_scan_run(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, int32_t fsmp, int32_t lsmp,
+                 int32_t available, float *kernel_ms) {
+  return scan_run_impl(ctx, L, O, fsmp, lsmp, available, kernel_ms, false, 0.f);
 }

@@ -31,20 +31,19 @@ def _window(shape, ijk, win):
     return lo, hi
 
 
-def spline_location(coa_map: np.ndarray, ijk, win: int = 5, upscale: int = 10):
+def spline_location_window(trim: np.ndarray, lo, ijk, win: int = 5, upscale: int = 10):
     """
-    ``_splineloc`` (scan.py:736-841): returns the fractional grid index of the interpolated peak,
-    or the gridded peak when the window touches the grid edge or the result leaves the window.
+    ``_splineloc`` (scan.py:736-841) on the window ``trim`` = ``coa_map[lo : lo + trim.shape]``:
+    returns the fractional grid index of the interpolated peak, or the gridded peak when the
+    window touches the grid edge or the result leaves the window.
     """
     from scipy.interpolate import Rbf
 
     ijk = np.asarray(ijk)
-    lo, hi = _window(coa_map.shape, ijk, win)
-    ext = [h - l for l, h in zip(lo, hi)]
+    ext = trim.shape
     if not (ext[0] == ext[1] == ext[2]):
         logging.info("\t !!!! Spline error: interpolation window crosses edge of grid !!!!")
         return ijk.astype(float)
-    trim = coa_map[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]]
     axes = [np.linspace(0, n - 1, n) for n in trim.shape]
     # NB: the reference builds its sample grid with numpy.meshgrid's default 'xy' indexing
     # (scan.py:777, :797) and flattens the data in C order; reproduce exactly that pairing.
@@ -61,14 +60,19 @@ def spline_location(coa_map: np.ndarray, ijk, win: int = 5, upscale: int = 10):
     return peak
 
 
-def gaussian_fit(smoothed: np.ndarray, ijk, mean: float, thresh: float = 0.0, win: int = 7):
+def spline_location(coa_map: np.ndarray, ijk, win: int = 5, upscale: int = 10):
+    """``_splineloc`` on a full host map: cut the window, then :func:`spline_location_window`."""
+    lo, hi = _window(coa_map.shape, ijk, win)
+    return spline_location_window(coa_map[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]], lo, ijk, win, upscale)
+
+
+def gaussian_fit_window(sub: np.ndarray, lo, ijk, mean: float, thresh: float = 0.0):
     """
-    ``_gaufit3d`` (scan.py:844-936): fit ``-log(map - mean) = quadratic(x, y, z)`` over the window
-    nodes above ``thresh``; returns (fractional grid index of the expectation, 1-sigma in nodes).
+    ``_gaufit3d`` (scan.py:844-936) on the window ``sub`` = ``smoothed[lo : lo + sub.shape]`` around
+    the peak ``ijk``: fit ``-log(map - mean) = quadratic(x, y, z)`` over the window nodes above
+    ``thresh``; returns (fractional grid index of the expectation, 1-sigma in nodes).
     """
-    shape = smoothed.shape
-    lo, hi = _window(shape, ijk, win)
-    sub = smoothed[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]]
+    hi = [l + n for l, n in zip(lo, sub.shape)]
     keep = sub > thresh                                             # scan.py:873 (on the raw map)
     gx, gy, gz = np.meshgrid(*[np.arange(l, h) - c for l, h, c in zip(lo, hi, ijk)], indexing="ij")
     x, y, z = gx[keep].astype(float), gy[keep].astype(float), gz[keep].astype(float)
@@ -88,31 +92,75 @@ def gaussian_fit(smoothed: np.ndarray, ijk, mean: float, thresh: float = 0.0, wi
     return loc + np.asarray(ijk), sigma_nodes
 
 
-def calculate_location(coa_map_sum: np.ndarray, lut, engine, return_maps: bool = False) -> dict:
-    """
-    ``_calculate_location`` (scan.py:696-733).  ``coa_map_sum`` is the un-normalised marginal map.
-    Returns a dict with ``coa_map`` (normalised, scan.py:720-721), ``spline`` location,
-    ``gaussian`` (location, uncertainty), ``covariance`` (location, uncertainty).
-    """
-    coa_map = coa_map_sum / np.nanmax(coa_map_sum)
-    ijk, _, _ = engine.map_peak(coa_map)
+def gaussian_fit(smoothed: np.ndarray, ijk, mean: float, thresh: float = 0.0, win: int = 7):
+    """``_gaufit3d`` on a full host map: cut the window, then :func:`gaussian_fit_window`."""
+    lo, hi = _window(smoothed.shape, ijk, win)
+    return gaussian_fit_window(smoothed[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]], lo, ijk, mean, thresh)
 
-    spline_idx = spline_location(coa_map, ijk)
+
+def _finish(lut, spline_idx, gau_idx, gau_sigma, expect, cov, ijk):
     spline_loc = lut.index2coord([list(spline_idx)])[0]
-
-    smoothed = engine.gaufilt3d(coa_map)
-    s_ijk, _, s_mean = engine.map_peak(smoothed)
-    gau_idx, gau_sigma = gaussian_fit(smoothed, s_ijk, s_mean)
     gau_loc = lut.index2coord([list(gau_idx)])[0]
     gau_unc = gau_sigma * np.asarray(lut.node_spacing)
-
-    expect, cov = engine.covfit3d(coa_map, lut.node_spacing, thresh=0.90)
     cov_xyz = np.asarray(lut.ll_corner) + expect                    # scan.py:1001
     cov_loc = lut.grid2coord(np.atleast_2d(cov_xyz))[0] if getattr(lut, "grid2coord", None) else cov_xyz
     cov_unc = np.diag(np.sqrt(np.abs(cov)))                         # scan.py:1003
+    return {"spline": spline_loc, "gaussian": (gau_loc, gau_unc), "covariance": (cov_loc, cov_unc),
+            "peak_index": ijk}
 
-    out = {"spline": spline_loc, "gaussian": (gau_loc, gau_unc), "covariance": (cov_loc, cov_unc),
-           "peak_index": ijk}
+
+def calculate_location_device(coa_map_sum, lut, return_maps: bool = False) -> dict:
+    """
+    ``_calculate_location`` (scan.py:696-733) on a :class:`~quakemigrate_b200.core.DeviceMap`
+    holding the un-normalised marginal map: the map is normalised, smoothed and reduced on the
+    device; only the peak (32 B), the 5^3 spline window, the 7^3 Gaussian-fit window and the 12
+    covariance moments cross PCIe (< 5 KB per event; ``pcie_bytes`` in the result).
+    """
+    coa = coa_map_sum.normalise()                                   # scan.py:720-721
+    ijk, _, _ = coa.peak()
+    lo, hi = _window(coa.shape, ijk, 5)
+    trim = coa.window(lo, hi)
+    spline_idx = spline_location_window(trim, lo, ijk)
+
+    smoothed = coa.gaufilt()
+    s_ijk, _, s_mean = smoothed.peak()
+    lo7, hi7 = _window(coa.shape, s_ijk, 7)
+    sub = smoothed.window(lo7, hi7)
+    gau_idx, gau_sigma = gaussian_fit_window(sub, lo7, s_ijk, s_mean)
+
+    expect, cov = coa.covfit(lut.node_spacing, thresh=0.90)
+    out = _finish(lut, spline_idx, gau_idx, gau_sigma, expect, cov, ijk)
+    out["pcie_bytes"] = int(2 * 32 + trim.nbytes + sub.nbytes + 12 * 8 + 2 * 7 * 8)
+    if return_maps:
+        out["coa_map"], out["smoothed"] = coa.fetch(), smoothed.fetch()
+    smoothed.free()
+    return out
+
+
+def calculate_location(coa_map_sum, lut, engine, return_maps: bool = False) -> dict:
+    """
+    ``_calculate_location`` (scan.py:696-733).  ``coa_map_sum`` is the un-normalised marginal map:
+    a device map (the product path, see :func:`calculate_location_device`) or a host array, which
+    is uploaded once when the engine can keep maps on the device.
+    Returns a dict with ``spline`` location, ``gaussian`` (location, uncertainty), ``covariance``
+    (location, uncertainty) and, with ``return_maps``, ``coa_map`` (normalised) and ``smoothed``.
+    """
+    if hasattr(coa_map_sum, "normalise"):
+        return calculate_location_device(coa_map_sum, lut, return_maps)
+    if hasattr(engine, "upload_map"):
+        dev = engine.upload_map(coa_map_sum)
+        try:
+            return calculate_location_device(dev, lut, return_maps)
+        finally:
+            dev.free()
+    coa_map = coa_map_sum / np.nanmax(coa_map_sum)
+    ijk, _, _ = engine.map_peak(coa_map)
+    spline_idx = spline_location(coa_map, ijk)
+    smoothed = engine.gaufilt3d(coa_map)
+    s_ijk, _, s_mean = engine.map_peak(smoothed)
+    gau_idx, gau_sigma = gaussian_fit(smoothed, s_ijk, s_mean)
+    expect, cov = engine.covfit3d(coa_map, lut.node_spacing, thresh=0.90)
+    out = _finish(lut, spline_idx, gau_idx, gau_sigma, expect, cov, ijk)
     if return_maps:
         out["coa_map"], out["smoothed"] = coa_map, smoothed
     return out

@@ -33,7 +33,7 @@ import numpy as np
 
 from .core import DeviceOnsets, Engine
 from .onsets import DataAvailabilityException, Onset
-from .synthetic import time2sample
+from .util import time2sample
 
 
 class LUTPhasesException(Exception):
@@ -51,7 +51,9 @@ def marginal_window_indices(max_coa: np.ndarray, marginal_window: float, samplin
     Returns ``(i0, i1, imax)`` with the map window ``[i0, i1)``.
     """
     imax = int(np.argmax(max_coa))
-    half = int(round(marginal_window * sampling_rate))
+    # rows with |DT - otime| <= mw are kept (an inclusive comparison of times, io/event.py:427-431):
+    # floor(mw * sr) samples per side, NOT round -- mw = 0.15 s at 50 Hz keeps 7, not 8
+    half = int(np.floor(marginal_window * sampling_rate + 1e-9))
     first = max(0, imax - half)
     last = min(len(max_coa) - 1, imax + half)
     return first, last, imax
@@ -158,7 +160,7 @@ class QuakeScan:
                 dev.free()
 
     def compute_locate(self, data, marginal_window: float | None = None, return_map4d: bool = False,
-                       fit_location: bool = False):
+                       fit_location: bool = False, return_coa_map: bool = True):
         """
         Fast locate: the max-coalescence traces over the whole span, then only the marginal
         window around the peak (io/event.py:421-439) is re-migrated on the device.
@@ -166,7 +168,9 @@ class QuakeScan:
         Returns a dict with ``times``, ``max_coa``, ``max_coa_n``, ``coord``, ``window`` =
         ``(i0, i1)``, ``coa_map`` = ``sum_t map4d[..., i0:i1]`` (scan.py:720; divide by its
         ``nanmax`` for the normalised map of scan.py:721), optionally ``map4d`` (the window slab),
-        and ``onset_data``.
+        and ``onset_data``.  With ``fit_location`` (and no slab requested) the map stays on the
+        device for the location fits; ``return_coa_map=False`` then skips its 8*N-byte copy to the
+        host altogether.
         """
         mw = self.marginal_window if marginal_window is None else marginal_window
         onsets, onset_data, dlut, dev, owned, fsmp, lsmp, avail = self._prepare(data)
@@ -183,16 +187,26 @@ class QuakeScan:
                 "coord": self.lut.index2coord(max_idx, unravel=True),
                 "window": (i0, i1), "peak_sample": imax, "onset_data": onset_data,
             }
-            if i1 > i0:
-                res = self.engine.locate_window(dlut, dev, fsmp, lsmp, avail, i0, i1, return_map4d=return_map4d)
-                out["coa_map"], out["map4d"] = (res if return_map4d else (res, None))
-            else:  # degenerate single-row window: the reference slices an empty map
+            if i1 <= i0:  # degenerate single-row window: the reference slices an empty map
                 out["coa_map"] = np.zeros(dlut.shape[:-1])
                 out["map4d"] = np.zeros(dlut.shape[:-1] + (0,)) if return_map4d else None
-            if fit_location and i1 > i0:
-                # _calculate_location (scan.py:696-733): spline / Gaussian / covariance estimates
+            elif fit_location and not return_map4d and hasattr(self.engine, "locate_window_device"):
+                # the marginal map never leaves the device: _calculate_location (scan.py:696-733)
+                # gets its windows and moments from the handle (a few KB over PCIe per event)
                 from .locate import calculate_location
-                out["location"] = calculate_location(out["coa_map"], self.lut, self.engine)
+                dmap = self.engine.locate_window_device(dlut, dev, fsmp, lsmp, avail, i0, i1)
+                try:
+                    out["coa_map"] = dmap.fetch() if return_coa_map else None
+                    out["map4d"] = None
+                    out["location"] = calculate_location(dmap, self.lut, self.engine)
+                finally:
+                    dmap.free()
+            else:
+                res = self.engine.locate_window(dlut, dev, fsmp, lsmp, avail, i0, i1, return_map4d=return_map4d)
+                out["coa_map"], out["map4d"] = (res if return_map4d else (res, None))
+                if fit_location:
+                    from .locate import calculate_location
+                    out["location"] = calculate_location(out["coa_map"], self.lut, self.engine)
             return out
         finally:
             if owned:

@@ -19,20 +19,12 @@ import dataclasses
 
 import numpy as np
 
+from .util import time2sample, trim2sample  # noqa: F401  (re-exported for the tests)
+
 
 # ------------------------------------------------------------------------------------------
 # pad -> sample arithmetic (host logic mirrored from the reference)
 # ------------------------------------------------------------------------------------------
-def time2sample(time: float, sampling_rate: int) -> int:
-    """``quakemigrate.util.time2sample`` (util.py:152-172)."""
-    return int(round(time * int(sampling_rate)))
-
-
-def trim2sample(time: float, sampling_rate: int) -> float:
-    """``quakemigrate.util.trim2sample`` (util.py:248-269)."""
-    return int(np.ceil(time * sampling_rate) / sampling_rate * 1000) / 1000
-
-
 def stalta_pads(sta: float, lta: float, max_traveltime: float, timespan: float,
                 sampling_rate: int) -> tuple[float, float]:
     """
