@@ -6,16 +6,20 @@ Benchmark of the coalescence hot path (fused migrate + stack + max-reduce) on B2
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference ...      # the reference's own OpenMP C path on host cores
+    python bench.py --workload cfg4           # locate path (mode "locate": span scan + marginal window + 3-D stage)
+    python bench.py --workload cfg2 --weak    # round-1 workload: one cfg2 slab per GPU stacked along x
 
 One "step" = one pass of the hot path over the workload: for every one of the N*T
 (node, sample) pairs stack S onset samples, exponentiate, and reduce over nodes to the per-sample
 (max, arg-max, normalised max) -- what QuakeScan._compute does per detect timestep
 (quakemigrate/signal/scan.py:635-638).  Metric: node-samples / second (whole job).
 
-Workload: BASELINE.json configs[1] (101x101x51 grid, 32 onset rows, 120000 samples @ 100 Hz,
-classic STA/LTA) per GPU; with N GPUs the grid is N such slabs stacked along x and sharded by
-x-slab (weak scaling), every rank ends with the global result after one NCCL all-gather of the
-per-sample candidates.
+Default workload: BASELINE.json configs[2] = north_star's target, 201x201x101 grid x 64 onset rows x
+360000 samples @ 100 Hz, classic STA/LTA, GRID-SHARDED over the GPUs (strong scaling: N=1 holds the
+whole grid, N=8 the survey's 8(e) split); every rank ends with the global result after one NCCL
+all-gather of the per-sample candidates.  At every N, rank 0 runs the compiled reference C on a few
+random 200-sample windows of the GLOBAL grid and the line carries the comparison
+(`parity_vs_reference_sample`); those runs are also the `cpu_baseline`.
 
 torch is used only for the torchrun rendezvous / barrier / max-over-ranks; the data path is
 libqmb200.so (own CUDA kernels, own NCCL communicator) driven through ctypes.
@@ -43,6 +47,7 @@ from quakemigrate_b200 import synthetic as syn  # noqa: E402
 CTRL_GROUP = None
 METRIC = "grid-nodes x samples / sec (migrate+stack+max-reduce)"
 UNIT = "node-samples/s"
+DEFAULT_WORKLOAD = "cfg3"
 
 
 def parse_args():
@@ -51,18 +56,30 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(syn.CONFIGS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(syn.CONFIGS))
+    ap.add_argument("--mode", default=None, choices=["detect", "locate"],
+                    help="detect: fused scan (default); locate: span scan + marginal window + 3-D map stage "
+                         "(default for --workload cfg4)")
     ap.add_argument("--variant", type=int, default=-1, help="kernel tiling variant id; -1 = library default")
     ap.add_argument("--samples", type=int, default=0, help="override n_samples (debug)")
     ap.add_argument("--precision", default=None, choices=["auto", "q16", "fp32"],
-                    help="operand format of the scan's gathers (library default: auto -> q16 at bench sizes)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+                    help="operand format of the scan's gathers (library default: auto -> verified q16)")
+    ap.add_argument("--no-cpu-baseline", action="store_true",
+                    help="skip the reference-C parity windows / CPU baseline (profiling runs)")
     ap.add_argument("--pre-only", action="store_true",
                     help="profiling aid: run only the pre-processing stage on the workload's full-length traces")
-    ap.add_argument("--strong", action="store_true",
-                    help="strong scaling: shard the FIXED workload grid over the ranks (default: weak, one "
-                         "workload-sized slab per GPU)")
-    return ap.parse_args()
+    ap.add_argument("--weak", action="store_true",
+                    help="weak scaling: one workload-sized slab per GPU stacked along x "
+                         "(default: strong, the FIXED workload grid sharded over the ranks)")
+    ap.add_argument("--strong", action="store_true", help="(default; kept for round-1 command lines)")
+    ap.add_argument("--e2e-steps", type=int, default=5,
+                    help="cap of the end-to-end loop (host buffers in and out); the device-timed loop runs --steps")
+    ap.add_argument("--parity-windows", type=int, default=3)
+    ap.add_argument("--parity-samples", type=int, default=200)
+    a = ap.parse_args()
+    if a.mode is None:
+        a.mode = "locate" if a.workload == "cfg4" else "detect"
+    return a
 
 
 def measured_peak_hbm():
@@ -75,10 +92,40 @@ def measured_peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def global_config(base: syn.SynthConfig, world: int, n_samples: int) -> syn.SynthConfig:
+def global_config(base: syn.SynthConfig, world: int, n_samples: int, weak: bool) -> syn.SynthConfig:
     nx, ny, nz = base.grid
+    if not weak:
+        return base.scaled(n_samples=n_samples or base.n_samples, name=base.name)
     return base.scaled(grid=(nx * world, ny, nz), n_samples=n_samples or base.n_samples,
                        name=f"{base.name}x{world}")
+
+
+def git_head() -> str:
+    try:
+        return subprocess.run(["git", "-C", str(ROOT), "rev-parse", "--short=12", "HEAD"], capture_output=True,
+                              text=True, timeout=5).stdout.strip() or "unknown"
+    except Exception:
+        return "unknown"
+
+
+def ncu_traffic(workload: str, variant: int, operand_bytes: int):
+    """
+    DRAM bytes per launch of k_scan from the committed `ncu --set full` capture of the SAME
+    (workload, tiling variant, operand format): profiles/scan_ncu_summary.json holds one entry per
+    key with the git revision it was captured at.  No entry -> null (never a number from another kernel).
+    """
+    prof = ROOT / "profiles" / "scan_ncu_summary.json"
+    if not prof.exists():
+        return None, None
+    try:
+        pj = json.loads(prof.read_text())
+    except Exception:
+        return None, None
+    key = f"{workload}:v{variant}:{'q16' if operand_bytes == 2 else 'fp32'}"
+    ent = (pj.get("entries") or {}).get(key)
+    if not ent:
+        return None, None
+    return ent.get("dram_bytes_per_launch"), {"key": key, "captured_at_git": ent.get("git"), "tag": ent.get("tag")}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -134,30 +181,24 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU side: the reference's own C path (oracle/_ref) or, where it was not built, the oracle port
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_sample(cfg: syn.SynthConfig, prob: syn.SynthProblem, onsets_lin: np.ndarray,
-                         t_sub: int, warm: int, reps: int, return_result: bool = False):
+def cpu_reference_window(traveltimes: np.ndarray, onsets_lin: np.ndarray, fsmp: int, lsmp: int, n_rows: int,
+                         t0: int, t_sub: int):
     """
-    Time migrate + find_max_coa of the reference on a bounded sample: the full grid, the first
-    `t_sub` output samples.  Returns (node-samples/s, kind, cores, seconds per rep).
+    migrate + find_max_coa of the reference (core/lib.py:53-170 semantics, incl. its fresh
+    np.zeros volume) for output samples [t0, t0 + t_sub) of the FULL grid `traveltimes`.
+    Returns ((max_coa, max_norm_coa, max_idx), seconds, kind, cores).
     """
-    from oracle import qm_oracle as O  # the ONE place bench.py touches oracle/: the CPU baseline
+    from oracle import qm_oracle as O  # bench.py touches oracle/ only in the CPU baseline / reference legs
 
     kind = "ref" if O.have("ref") else "port"
     cores = O.default_threads()
-    t_sub = min(t_sub, cfg.n_samples)
-    sub = np.ascontiguousarray(onsets_lin[:, : prob.fsmp + t_sub + prob.lsmp])
-    times = []
-    for i in range(warm + reps):
-        t0 = time.perf_counter()
-        m4 = O.migrate(sub, prob.traveltimes, prob.fsmp, prob.lsmp, cfg.n_rows, threads=cores, kind=kind)
-        result = O.find_max_coa(m4, threads=cores, kind=kind)
-        dt = time.perf_counter() - t0
-        del m4
-        if i >= warm:
-            times.append(dt)
-    sec = float(np.median(times))
-    out = (cfg.n_nodes * t_sub / sec, ("reference" if kind == "ref" else "port"), cores, sec)
-    return out + (result,) if return_result else out
+    sub = np.ascontiguousarray(onsets_lin[:, t0: t0 + fsmp + t_sub + lsmp])
+    t_a = time.perf_counter()
+    m4 = O.migrate(sub, traveltimes, fsmp, lsmp, n_rows, threads=cores, kind=kind)
+    result = O.find_max_coa(m4, threads=cores, kind=kind)
+    sec = time.perf_counter() - t_a
+    del m4
+    return result, sec, ("reference" if kind == "ref" else "port"), cores
 
 
 def host_onsets(prob: syn.SynthProblem, position: str) -> np.ndarray:
@@ -169,15 +210,19 @@ def host_onsets(prob: syn.SynthProblem, position: str) -> np.ndarray:
     return syn.onsets_from_waveforms(prob, lambda x, a, b: fn(x, a, b, kind=kind))
 
 
+def reference_sample_size(cfg: syn.SynthConfig) -> int:
+    """Output samples per reference step: the float64 volume stays near 6 GB, a step near 2-6 s."""
+    return int(max(50, min(400, (6.5e9 / 8.0) // cfg.n_nodes)))
+
+
 def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
-    cfg = global_config(syn.CONFIGS[args.workload], world, args.samples)
-    t_sub = 400
-    # only the first fsmp + t_sub + lsmp samples are ever touched: build a short problem with the
-    # same geometry / LUT / pads
+    cfg = global_config(syn.CONFIGS[args.workload], world, args.samples, args.weak)
+    t_sub = reference_sample_size(cfg)
+    # only the first fsmp + t_sub + lsmp samples are ever touched: the full-size geometry / LUT /
+    # pads, and waveforms of just that length
     prob = syn.make_problem(cfg, with_waveforms=False)
-    short = cfg.scaled(n_samples=t_sub, name=cfg.name)
     rng = np.random.default_rng(100 + cfg.seed)
     n_sta = len(prob.stations_xyz)
     prob.waveforms = rng.standard_normal((3 * n_sta, prob.fsmp + t_sub + prob.lsmp))
@@ -185,7 +230,7 @@ def run_reference(args, rank: int, world: int):
     per_step = []
     kind = cores = None
     for i in range(args.warmup + args.steps):
-        v, kind, cores, sec = cpu_reference_sample(short, prob, onsets, t_sub, 0, 1)
+        _, sec, kind, cores = cpu_reference_window(prob.traveltimes, onsets, prob.fsmp, prob.lsmp, cfg.n_rows, 0, t_sub)
         if i >= args.warmup:
             per_step.append(sec)
     sec = float(np.mean(per_step))
@@ -193,14 +238,14 @@ def run_reference(args, rank: int, world: int):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak" if args.weak else "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{cfg.name}: {cfg.grid[0]}x{cfg.grid[1]}x{cfg.grid[2]} grid, "
                                f"{cfg.n_rows} rows, bounded sample of {t_sub} of {cfg.n_samples} samples per step",
                    "n_nodes": cfg.n_nodes, "n_rows": cfg.n_rows, "n_samples": cfg.n_samples},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                         "sample": f"full grid x first {t_sub} samples, migrate+find_max_coa, "
-                                   f"{args.steps} timed steps after {args.warmup} warm-up"},
+                         "sample": f"full grid x first {t_sub} samples, migrate+find_max_coa (fresh zeroed volume per "
+                                   f"step like core/lib.py:101), {args.steps} timed steps after {args.warmup} warm-up"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -258,20 +303,61 @@ def preprocess_stage(eng, cfg, prob, args, peak, peak_src):
     return stage
 
 
+
 # ------------------------------------------------------------------------------------------------
-# GPU arm
+# parity of this run's result against the reference C, on random windows of the GLOBAL grid
+# ------------------------------------------------------------------------------------------------
+def parity_and_cpu_baseline(args, cfg, tt_global, prob, onsets_lin, res):
+    """
+    `res` = (max_coa, max_norm_coa, max_idx) of the e2e leg (the global result, identical on every
+    rank).  Runs the reference on `--parity-windows` windows of `--parity-samples` output samples at
+    seeded random offsets, compares, and times those runs (the CPU baseline of this line).
+    """
+    T, S = cfg.n_samples, cfg.n_rows
+    n_win, t_sub = max(1, args.parity_windows), min(args.parity_samples, T)
+    rng = np.random.default_rng(20260417)
+    starts = sorted(int(v) for v in rng.integers(0, max(1, T - t_sub + 1), size=n_win))
+    if n_win >= 2:  # always include the very first and the very last window (pads, tails)
+        starts[0], starts[-1] = 0, T - t_sub
+    worst = {"argmax_equal": True, "max_coa_max_rel": 0.0, "max_norm_coa_max_rel": 0.0}
+    secs, kind, cores = [], None, None
+    mismatches = 0
+    for t0 in starts:
+        ref, sec, kind, cores = cpu_reference_window(tt_global, onsets_lin, prob.fsmp, prob.lsmp, S, t0, t_sub)
+        secs.append(sec)
+        sl = slice(t0, t0 + t_sub)
+        eq = np.array_equal(res[2][sl], ref[2])
+        mismatches += int(np.sum(res[2][sl] != ref[2]))
+        worst["argmax_equal"] = bool(worst["argmax_equal"] and eq)
+        worst["max_coa_max_rel"] = max(worst["max_coa_max_rel"], float(np.max(np.abs(res[0][sl] - ref[0]) / ref[0])))
+        worst["max_norm_coa_max_rel"] = max(worst["max_norm_coa_max_rel"],
+                                            float(np.max(np.abs(res[1][sl] - ref[1]) / ref[1])))
+    sec = float(np.median(secs))
+    parity = {"windows": [[t0, t0 + t_sub] for t0 in starts], "samples": n_win * t_sub,
+              "argmax_mismatches": mismatches, **worst,
+              "tolerance": {"argmax": "bit-exact", "max_coa": 1e-5, "max_norm_coa": 1e-5},
+              "pass": bool(worst["argmax_equal"] and worst["max_coa_max_rel"] <= 1e-5 and
+                           worst["max_norm_coa_max_rel"] <= 1e-5),
+              "note": "e2e result of this run (global, all ranks) against the reference C on the full GLOBAL grid"}
+    cpu = {"value": cfg.n_nodes * t_sub / sec, "unit": UNIT, "cores": cores, "kind": kind,
+           "sample": f"full {cfg.grid[0]}x{cfg.grid[1]}x{cfg.grid[2]} grid x {t_sub}-sample windows at {starts} of {T} "
+                     f"samples, migrate+find_max_coa, median of {n_win} ({sec:.2f} s each)"}
+    return parity, cpu
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm: detect
 # ------------------------------------------------------------------------------------------------
 def run_ours(args, rank: int, world: int, local_rank: int, dist):
     from quakemigrate_b200.core import Engine
+    from quakemigrate_b200.sharding import slab_bounds
 
     base = syn.CONFIGS[args.workload]
-    if args.strong:
-        from quakemigrate_b200.sharding import slab_bounds
-        cfg = base.scaled(n_samples=args.samples or base.n_samples, name=base.name)
-        x0, x1 = slab_bounds(cfg.grid[0], world, rank)
-    else:
-        cfg = global_config(base, world, args.samples)
+    cfg = global_config(base, world, args.samples, args.weak)
+    if args.weak:
         x0, x1 = rank * base.grid[0], (rank + 1) * base.grid[0]
+    else:
+        x0, x1 = slab_bounds(cfg.grid[0], world, rank)
     prob = syn.make_problem(cfg, with_waveforms=True, x_range=(x0, x1))
     N_local = (x1 - x0) * cfg.grid[1] * cfg.grid[2]
     N_global, T, S = cfg.n_nodes, cfg.n_samples, cfg.n_rows
@@ -279,8 +365,7 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
 
     eng = Engine(local_rank, variant=args.variant if args.variant >= 0 else None, precision=args.precision)
     if args.pre_only:
-        full = syn.make_problem(global_config(base, 1, 0), with_waveforms=True)
-        print(json.dumps(preprocess_stage(eng, base, full, args, *measured_peak_hbm())), flush=True)
+        print(json.dumps(preprocess_stage(eng, base, prob, args, *measured_peak_hbm())), flush=True)
         eng.close()
         return
     if world > 1:
@@ -305,40 +390,45 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
     barrier()
     sampler.start()
     launches0 = eng.launch_count
-    scan_ms, total_ms, slow = [], [], 0
+    scan_ms, total_ms, tail_ms, slow, syncs = [], [], [], 0, 0
     wall0 = time.perf_counter()
     for _ in range(args.steps):
         eng.flush_l2()
         ms = eng.detect_device(lut, dev_on, prob.fsmp, prob.lsmp, S)
         scan_ms.append(ms["scan_ms"])
         total_ms.append(ms["total_ms"])
+        tail_ms.append(ms["finalize_ms"])
         slow = max(slow, ms["slow_samples"])
+        syncs = max(syncs, eng.last_scan_info["host_syncs_in_timed_region"])
     barrier()
     wall = time.perf_counter() - wall0
     launches = eng.launch_count - launches0  # own kernels only (L2 flushes are memsets)
     clocks = sampler.stop()
     dev_total_ms = float(np.sum(total_ms))
+    scan_info = eng.last_scan_info
 
     # ---- end-to-end through the host-buffer call: `e2e` ----------------------------------------
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
     Engine.pin(onsets_lin)
-    for _ in range(2):
-        eng.detect(lut, onsets_lin, prob.fsmp, prob.lsmp, S)
+    eng.detect(lut, onsets_lin, prob.fsmp, prob.lsmp, S)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         res = eng.detect(lut, onsets_lin, prob.fsmp, prob.lsmp, S)
     barrier()
-    e2e_sec = (time.perf_counter() - t0) / args.steps
+    e2e_sec = (time.perf_counter() - t0) / e2e_steps
     Engine.unpin(onsets_lin)
 
     # ---- max over ranks ----------------------------------------------------------------------
     if world > 1:
         import torch
-        t = torch.tensor([dev_total_ms, e2e_sec, float(np.mean(scan_ms)), wall], dtype=torch.float64)
+        t = torch.tensor([dev_total_ms, e2e_sec, float(np.mean(scan_ms)), wall, float(np.mean(tail_ms)), float(slow)],
+                         dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=CTRL_GROUP)
-        dev_total_ms, e2e_sec, scan_mean, wall = [float(x) for x in t]
+        dev_total_ms, e2e_sec, scan_mean, wall, tail_mean, slow = [float(x) for x in t]
+        slow = int(slow)
     else:
-        scan_mean = float(np.mean(scan_ms))
+        scan_mean, tail_mean = float(np.mean(scan_ms)), float(np.mean(tail_ms))
     ms_per_step = dev_total_ms / args.steps
     value = N_global * T / (ms_per_step * 1e-3)
 
@@ -346,51 +436,52 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
     peak, peak_src = measured_peak_hbm()
     b_alg = 4.0 * N_local * T * (S + 1) + 4.0 * N_local * S + 4.0 * S * P
     achieved = b_alg / (scan_mean * 1e-3) / 1e9
-    traffic = None
-    prof = ROOT / "profiles" / "scan_ncu_summary.json"
-    if prof.exists():
-        try:
-            pj = json.loads(prof.read_text())
-            if pj.get("workload") == base.name:
-                traffic = pj.get("dram_bytes_per_launch")
-        except Exception:
-            pass
+    bpg = eng.last_scan_bytes_per_gather
+    traffic, traffic_src = (None, None)
+    if world == 1 and not args.samples:
+        traffic, traffic_src = ncu_traffic(base.name, info["variant"], bpg)
     measured_pipe = eng.smem_pipe_peak()
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     ga = float(N_local) * T * S / (scan_mean * 1e-3)
     smem_peak = 148 * 32 * sm_mhz * 1e6
     # shared-memory bytes one gathered operand costs: 4 (float32 rows) or 2 (16-bit fixed-point
     # rows, two samples per LDS.32); the pipe moves 128 B/clk/SM either way
-    bpg = eng.last_scan_bytes_per_gather
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "strong" if args.strong else "weak",
+        "scaling": "weak" if args.weak else "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {
             "workload": f"{cfg.name}: {cfg.grid[0]}x{cfg.grid[1]}x{cfg.grid[2]} grid "
                         f"({x1 - x0}x{cfg.grid[1]}x{cfg.grid[2]} x-slab on rank {rank}), {S} onset rows, "
                         f"{T} samples @ {cfg.sampling_rate} Hz, {cfg.position} STA/LTA, detect() scan",
             "n_nodes": N_global, "n_rows": S, "n_samples": T, "fsmp": prob.fsmp, "lsmp": prob.lsmp,
-            "parallelism": f"node-slab x{world}", "cache": "L2 flushed (256 MiB memset) before every timed step",
+            "parallelism": f"node-slab x{world} ({'one workload-sized slab per GPU' if args.weak else 'fixed grid sharded by x-planes'})",
+            "cache": "L2 flushed (256 MiB memset) before every timed step",
             "nodes_per_tile": info["nodes_per_tile"], "max_tile_span": info["max_tile_span"],
             "variant": info["variant"], "duplicate_fraction": round(info["duplicate_fraction"], 4),
-            "scan_operands": "16-bit fixed point (2 per LDS.32)" if bpg == 2 else "float32",
-            "timing": "sum of per-step CUDA-event times on the launching stream, max over ranks",
+            "scan_operands": "16-bit fixed point (2 per LDS.32), node sums verified against float32 windows"
+                             if bpg == 2 else "float32",
+            "timing": "sum of per-step CUDA-event times on the launching stream (scan + merge + exchange + "
+                      "candidates + slow path + verification windows), max over ranks",
+            "git": git_head(),
         },
         "e2e": {"value": N_global * T / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": int(onsets_lin.nbytes),
-                "d2h_bytes_per_step": int(3 * 8 * T),
-                "note": "Engine.detect(): host float64 onsets -> H2D -> clip/log -> scan -> reduce -> D2H; "
-                        "travel-time table resident (uploaded once per availability pattern)"},
+                "d2h_bytes_per_step": int(3 * 8 * T), "steps": e2e_steps,
+                "note": "Engine.detect(): pinned host float64 onsets -> H2D -> clip/log/quantise -> scan -> reduce -> "
+                        "D2H of the three traces, wall clock between device synchronisations and rank barriers; "
+                        "travel-time table resident (uploaded once per availability pattern); loop capped at "
+                        "--e2e-steps"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic, "kernel": "k_scan", "kernel_ms": scan_mean, "peak_source": peak_src,
-            "algorithmic_bytes_per_launch": b_alg,
+            "traffic": traffic, "traffic_source": traffic_src, "kernel": "k_scan", "kernel_ms": scan_mean,
+            "peak_source": peak_src, "algorithmic_bytes_per_launch": b_alg,
             "note": "effective bandwidth per SURVEY 8(d): operands are served from shared memory after "
-                    "one compulsory HBM pass, so frac may exceed 1; the binding pipe is shared memory",
+                    "one compulsory HBM pass, so frac may exceed 1; the binding resources are the "
+                    "shared-memory pipe and instruction issue (smem_pipe below)",
             "smem_pipe": {"achieved_gather_adds_per_s": ga, "bytes_per_gather": bpg,
                           "peak_gather_adds_per_s": smem_peak * 4 / bpg,
                           "peak_gather_adds_per_s_fp32_operands": smem_peak,
@@ -401,27 +492,236 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
         },
         "wall_s_timed_region": wall,
         "slow_path_samples": slow,
+        "tail_ms_per_step": tail_mean,
+        "scan": {"operand_bytes": scan_info["operand_bytes"], "fell_back_fp32": scan_info["fell_back_fp32"],
+                 "check_windows": scan_info["check_windows"], "check_samples": scan_info["check_samples"],
+                 "check_max_rel_err": scan_info["check_max_rel_err"], "check_ms": scan_info["check_ms"],
+                 "two_candidate_samples": scan_info["two_candidate_samples"],
+                 "host_syncs_in_timed_region": syncs},
     }
 
     if rank == 0 and world == 1:
         line["stages"] = {"preprocess": preprocess_stage(eng, cfg, prob, args, peak, peak_src)}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, kind, cores, sec, ref = cpu_reference_sample(cfg, prob, onsets_lin, 600, 1, 2, return_result=True)
-        n_cmp = len(ref[0])
-        line["parity_vs_reference_sample"] = {
-            "samples": n_cmp, "argmax_equal": bool(np.array_equal(res[2][:n_cmp], ref[2])),
-            "max_coa_max_rel": float(np.max(np.abs(res[0][:n_cmp] - ref[0]) / ref[0])),
-            "max_norm_coa_max_rel": float(np.max(np.abs(res[1][:n_cmp] - ref[1]) / ref[1])),
-            "note": "e2e result of this run against the reference C on the CPU-baseline sample"}
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
-                                "sample": f"full {cfg.grid[0]}x{cfg.grid[1]}x{cfg.grid[2]} grid x first 600 of {T} "
-                                          f"samples, migrate+find_max_coa, median of 2 after 1 warm-up ({sec:.2f} s each)"}
+    if rank == 0 and not args.no_cpu_baseline:
+        # the GLOBAL table on rank 0's host (the reference needs all nodes)
+        tt_global = prob.traveltimes if world == 1 else syn.make_traveltimes(cfg)[0]
+        line["parity_vs_reference_sample"], line["cpu_baseline"] = parity_and_cpu_baseline(
+            args, cfg, tt_global, prob, onsets_lin, res)
+        del tt_global
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
         print(json.dumps(line), flush=True)
     del res
     eng.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm: locate (BASELINE configs[3]): span scan -> marginal window -> 3-D map stage
+# ------------------------------------------------------------------------------------------------
+def run_locate(args, rank: int, world: int, local_rank: int, dist):
+    """
+    One step = one located event (QuakeScan._locate_events body, scan.py:508-531): the max traces
+    over the whole span (16-bit rows), otime -> marginal window (io/event.py:421-439), the window
+    re-migrated with float32 rows and summed over time on the device (scan.py:720), and
+    _calculate_location on the device-resident map (scan.py:696-733).  With N GPUs every rank
+    locates its own replica of the event ("replicas only": events are independent).
+    """
+    from quakemigrate_b200.core import Engine
+    from quakemigrate_b200.locate import calculate_location_device
+    from quakemigrate_b200.lut import Grid3D
+    from quakemigrate_b200.scan import marginal_window_indices
+
+    cfg = syn.CONFIGS[args.workload].scaled(n_samples=args.samples or None, name=args.workload)
+    prob = syn.make_problem(cfg, with_waveforms=True)
+    N, T, S = cfg.n_nodes, cfg.n_samples, cfg.n_rows
+    mw = 2.0  # QuakeScan.marginal_window default (scan.py:236)
+    eng = Engine(local_rank, variant=args.variant if args.variant >= 0 else None, precision=args.precision)
+    lut = eng.upload_lut(prob.traveltimes)
+    dev_on, onsets_lin = eng.onsets_from_waveforms(prob.waveforms, prob.row_channels, prob.nsta, prob.nlta,
+                                                   position=cfg.position, return_onsets=True)
+    grid = Grid3D(cfg.grid, [cfg.node_spacing_km] * 3, [0.0, 0.0, 0.0])
+    info = lut.info()
+
+    def event(dev, stamps=None):
+        """The device part of one event; returns (result dict, location)."""
+        ms = eng.detect_device(lut, dev, prob.fsmp, prob.lsmp, S)
+        mx, nm, ix = eng.detect_fetch(T)
+        i0, i1, imax = marginal_window_indices(mx, mw, cfg.sampling_rate)
+        if stamps is not None:
+            eng.sync(); stamps.append(time.perf_counter())
+        dmap = eng.locate_window_device(lut, dev, prob.fsmp, prob.lsmp, S, i0, i1)
+        if stamps is not None:
+            eng.sync(); stamps.append(time.perf_counter())
+        box = {}
+        loc = calculate_location_device(dmap, grid, engine_timer=lambda: box.setdefault("ms", eng.timer_stop()))
+        dmap.free()
+        return {"scan": ms, "window": (i0, i1), "peak_sample": imax, "idx": ix[imax], "device_ms": box["ms"]}, loc
+
+    for _ in range(max(1, args.warmup)):
+        eng.timer_start()
+        event(dev_on)
+    sampler = ClockSampler(local_rank)
+    eng.sync()
+    if world > 1:
+        dist.barrier()
+    sampler.start()
+    launches0 = eng.launch_count
+    dev_ms, scan_ms, stage = [], [], []
+    for _ in range(args.steps):
+        eng.flush_l2()
+        stamps = [time.perf_counter()]
+        eng.timer_start()
+        out, loc = event(dev_on, stamps)
+        stamps.append(time.perf_counter())
+        dev_ms.append(out["device_ms"])
+        scan_ms.append(out["scan"]["scan_ms"])
+        stage.append(np.diff(stamps))
+    eng.sync()
+    if world > 1:
+        dist.barrier()
+    launches = eng.launch_count - launches0
+    clocks = sampler.stop()
+
+    # ---- e2e: host onsets in, location out (H2D of the onsets, host fits included) ---------------
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    Engine.pin(onsets_lin)
+    t_e2e = []
+    for i in range(e2e_steps + 1):
+        eng.sync()
+        t0 = time.perf_counter()
+        d = eng.upload_onsets(onsets_lin)
+        eng.timer_start()
+        out, loc = event(d)
+        d.free()
+        eng.sync()
+        if i:
+            t_e2e.append(time.perf_counter() - t0)
+    Engine.unpin(onsets_lin)
+    e2e_sec = float(np.mean(t_e2e))
+    dev_total_ms = float(np.sum(dev_ms))
+    scan_mean = float(np.mean(scan_ms))
+    if world > 1:
+        import torch
+        t = torch.tensor([dev_total_ms, e2e_sec, scan_mean], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=CTRL_GROUP)
+        dev_total_ms, e2e_sec, scan_mean = [float(x) for x in t]
+    ms_per_step = dev_total_ms / args.steps
+    value = world * N * T / (ms_per_step * 1e-3)
+    st = np.median(np.array(stage), axis=0) * 1e3  # span pass, window pass, map stage + host fits (ms, wall)
+    i0, i1 = out["window"]
+    Wn = i1 - i0
+
+    peak, peak_src = measured_peak_hbm()
+    P = prob.n_total
+    b_alg = 4.0 * N * T * (S + 1) + 4.0 * N * S + 4.0 * S * P
+    achieved = b_alg / (scan_mean * 1e-3) / 1e9
+    bpg = eng.last_scan_bytes_per_gather
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    smem_peak = 148 * 32 * sm_mhz * 1e6
+    ga = float(N) * T * S / (scan_mean * 1e-3)
+    win_hbm = 8.0 * N + 2.0 * N * S + 4.0 * S * (Wn + prob.lsmp)  # map written + tau16 tiles read + row windows
+    planted = np.unravel_index(prob.events[0][0], cfg.grid)
+    found = np.unravel_index(int(out["idx"]), cfg.grid)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": f"{cfg.name} locate: {cfg.grid[0]}x{cfg.grid[1]}x{cfg.grid[2]} grid, {S} onset rows, "
+                        f"{T} samples @ {cfg.sampling_rate} Hz, {cfg.position} STA/LTA, marginal window "
+                        f"{Wn} samples, Gaussian / covariance / spline location fits",
+            "mode": "locate", "n_nodes": N, "n_rows": S, "n_samples": T, "window_samples": Wn,
+            "parallelism": "one event per GPU (replicas only)" if world > 1 else "1 GPU",
+            "cache": "L2 flushed (256 MiB memset) before every timed step",
+            "variant": info["variant"], "timing": "CUDA events on the launching stream from the span scan to the "
+            "last device operation of the event (host gaps between them included), max over ranks",
+            "git": git_head(),
+        },
+        "e2e": {"value": world * N * T / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": int(onsets_lin.nbytes),
+                "d2h_bytes_per_step": int(3 * 8 * T + loc["pcie_bytes"]), "steps": e2e_steps,
+                "seconds_per_event": e2e_sec,
+                "note": "pinned host onsets -> H2D -> span scan -> D2H of the traces -> window pass -> device map "
+                        "stage -> windows/moments D2H -> host fits (RBF spline, pinv)"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "kernel": "k_scan (span pass)", "kernel_ms": scan_mean, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": b_alg,
+            "note": "effective bandwidth per SURVEY 8(d), see the detect line; shared-memory pipe fraction below",
+            "smem_pipe": {"achieved_gather_adds_per_s": ga, "bytes_per_gather": bpg,
+                          "frac": ga * bpg / (smem_peak * 4), "sm_mhz_used": sm_mhz},
+        },
+        "stages": {
+            "span_pass_ms": float(st[0]), "window_pass_ms": float(st[1]), "map_stage_and_fits_ms": float(st[2]),
+            "window_pass": {
+                "what": "k_scan MODE 1 on float32 rows: exp(stack/available) summed over the window per node",
+                "roofline": {"bound": "hbm", "achieved": win_hbm / (st[1] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": win_hbm / (st[1] * 1e-3) / 1e9 / peak, "true_hbm_bytes_model": win_hbm,
+                             "note": "true HBM bytes (8 N written, table and row windows read once); the pass is "
+                                     "bound by the shared-memory pipe like the scan: gather-adds/s below"},
+                "gather_adds_per_s": float(N) * Wn * S / (st[1] * 1e-3)},
+            "location_pcie_bytes_per_event": loc["pcie_bytes"],
+        },
+        "result": {"peak_node": [int(v) for v in found], "planted_node": [int(v) for v in planted],
+                   "peak_sample": int(out["peak_sample"]), "planted_origin_sample": int(prob.events[0][1]),
+                   "gaussian_location_km": [float(v) for v in loc["gaussian"][0]],
+                   "gaussian_uncertainty_km": [float(v) for v in loc["gaussian"][1]],
+                   "covariance_location_km": [float(v) for v in loc["covariance"][0]],
+                   "spline_location_km": [float(v) for v in loc["spline"]]},
+        "slow_path_samples": int(out["scan"]["slow_samples"]),
+    }
+    if rank == 0 and not args.no_cpu_baseline:
+        line["cpu_baseline"], line["parity_vs_reference_sample"] = locate_cpu_baseline(
+            args, cfg, prob, onsets_lin, eng, lut, dev_on, i0, i1, out)
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    eng.close()
+
+
+def locate_cpu_baseline(args, cfg, prob, onsets_lin, eng, lut, dev_on, i0, i1, out):
+    """
+    The reference's locate arithmetic on a bounded sample, timed on the host cores: migrate +
+    find_max_coa on 100 span samples (the per-sample cost of the span pass), migrate on the first
+    64 samples of the marginal window + np.sum(axis=-1) (scan.py:720), and _gaufilt3d
+    (scan.py:1008-1043, oracle restatement) on the full map.  Extrapolated linearly to one event.
+    The window leg doubles as the parity check of the device's marginal map.
+    """
+    from oracle import qm_oracle as O
+
+    N, T, S = cfg.n_nodes, cfg.n_samples, cfg.n_rows
+    t_span = min(100, T)
+    ref, sec_span, kind, cores = cpu_reference_window(prob.traveltimes, onsets_lin, prob.fsmp, prob.lsmp, S, 0, t_span)
+    w_sub = min(64, i1 - i0)
+    k = "ref" if O.have("ref") else "port"
+    sub = np.ascontiguousarray(onsets_lin[:, i0: i0 + prob.fsmp + w_sub + prob.lsmp])
+    t_a = time.perf_counter()
+    m4 = O.migrate(sub, prob.traveltimes, prob.fsmp, prob.lsmp, S, threads=cores, kind=k)
+    coa_ref = m4.sum(axis=-1)
+    sec_win = time.perf_counter() - t_a
+    del m4
+    got = eng.locate_window(lut, dev_on, prob.fsmp, prob.lsmp, S, i0, i0 + w_sub)
+    rel = float(np.max(np.abs(got - coa_ref) / coa_ref))
+    t_a = time.perf_counter()
+    O.np_gaufilt3d(coa_ref / coa_ref.max())
+    sec_gau = time.perf_counter() - t_a
+    res = eng.detect_fetch(T)
+    est = sec_span / t_span * T + sec_win / w_sub * (i1 - i0) + sec_gau
+    cpu = {"value": N * T / est, "unit": UNIT, "cores": cores, "kind": kind,
+           "seconds_per_event_extrapolated": est,
+           "sample": f"span: full grid x {t_span} of {T} samples ({sec_span:.2f} s); window: full grid x {w_sub} of "
+                     f"{i1 - i0} samples + sum over time ({sec_win:.2f} s); _gaufilt3d of the full map, oracle "
+                     f"restatement ({sec_gau:.2f} s); extrapolated linearly in samples"}
+    parity = {"span_samples": t_span, "argmax_equal": bool(np.array_equal(res[2][:t_span], ref[2])),
+              "max_coa_max_rel": float(np.max(np.abs(res[0][:t_span] - ref[0]) / ref[0])),
+              "max_norm_coa_max_rel": float(np.max(np.abs(res[1][:t_span] - ref[1]) / ref[1])),
+              "window_samples": w_sub, "coa_map_max_rel": rel,
+              "tolerance": {"argmax": "bit-exact", "values": 1e-5}}
+    parity["pass"] = bool(parity["argmax_equal"] and parity["max_coa_max_rel"] <= 1e-5 and
+                          parity["max_norm_coa_max_rel"] <= 1e-5 and rel <= 1e-5)
+    return cpu, parity
 
 
 def main():
@@ -446,7 +746,10 @@ def main():
         CTRL_GROUP = dist.new_group(backend="gloo")  # control plane: ids, timings (CPU tensors)
     elif args.gpus > 1:
         raise SystemExit("launch multi-GPU runs with torch.distributed.run (see the module docstring)")
-    run_ours(args, rank, world, local_rank, dist)
+    if args.mode == "locate":
+        run_locate(args, rank, world, local_rank, dist)
+    else:
+        run_ours(args, rank, world, local_rank, dist)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -131,6 +131,11 @@ int qmb_ctx_launch_count(qmb_ctx_t ctx, int64_t *count);
 /* benchmarking helpers: evict L2 by writing a 256 MiB scratch buffer; page-lock caller memory
  * so that H2D/D2H copies of host buffers run at full PCIe rate (cudaHostRegister). */
 int qmb_ctx_flush_l2(qmb_ctx_t ctx);
+/* CUDA-event stopwatch on the context's stream (where all kernels of this library are launched):
+ * start records an event, stop records a second one, waits for it and returns the device time
+ * between them (host gaps between the bracketed calls included). */
+int qmb_ctx_timer_start(qmb_ctx_t ctx);
+int qmb_ctx_timer_stop(qmb_ctx_t ctx, float *ms);
 int qmb_host_register(void *ptr, int64_t bytes);
 int qmb_host_unregister(void *ptr);
 

@@ -87,6 +87,8 @@ SIGNATURES = {
     "qmb_ctx_last_scan_info": (ctypes.c_int, [c_void_p, ctypes.POINTER(ScanInfo)]),
     "qmb_ctx_launch_count": (ctypes.c_int, [c_void_p, ctypes.POINTER(c_int64)]),
     "qmb_ctx_flush_l2": (ctypes.c_int, [c_void_p]),
+    "qmb_ctx_timer_start": (ctypes.c_int, [c_void_p]),
+    "qmb_ctx_timer_stop": (ctypes.c_int, [c_void_p, ctypes.POINTER(ctypes.c_float)]),
     "qmb_host_register": (ctypes.c_int, [c_void_p, c_int64]),
     "qmb_host_unregister": (ctypes.c_int, [c_void_p]),
     "qmb_comm_unique_id": (ctypes.c_int, [ctypes.c_char_p]),

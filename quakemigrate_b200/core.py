@@ -354,6 +354,16 @@ class Engine:
         _lib.check(self._lib.qmb_microbench_smem_pipe(self._h, int(iters), ctypes.byref(out)))
         return out.value
 
+    def timer_start(self):
+        """Record a CUDA event on the engine's stream (see :meth:`timer_stop`)."""
+        _lib.check(self._lib.qmb_ctx_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        """Device milliseconds since :meth:`timer_start` (CUDA events on the launching stream)."""
+        ms = ctypes.c_float(0.0)
+        _lib.check(self._lib.qmb_ctx_timer_stop(self._h, ctypes.byref(ms)))
+        return ms.value
+
     def flush_l2(self):
         """Evict L2 (benchmark hygiene between timed iterations)."""
         _lib.check(self._lib.qmb_ctx_flush_l2(self._h))

@@ -102,6 +102,28 @@ extern "C" int qmb_ctx_sync(qmb_ctx_t ctx) {
   return QMB_OK;
 }
 
+// CUDA-event stopwatch on the context's stream (the stream every kernel of this library runs on)
+extern "C" int qmb_ctx_timer_start(qmb_ctx_t ctx) {
+  if (!ctx) QMB_FAIL(QMB_ERR_ARG, "null context");
+  QMB_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->ev_user[0]) {
+    QMB_CUDA(cudaEventCreate(&ctx->ev_user[0]));
+    QMB_CUDA(cudaEventCreate(&ctx->ev_user[1]));
+  }
+  QMB_CUDA(cudaEventRecord(ctx->ev_user[0], ctx->stream));
+  return QMB_OK;
+}
+
+extern "C" int qmb_ctx_timer_stop(qmb_ctx_t ctx, float *ms) {
+  if (!ctx || !ms) QMB_FAIL(QMB_ERR_ARG, "null argument");
+  if (!ctx->ev_user[0]) QMB_FAIL(QMB_ERR_STATE, "timer was not started");
+  QMB_CUDA(cudaSetDevice(ctx->device));
+  QMB_CUDA(cudaEventRecord(ctx->ev_user[1], ctx->stream));
+  QMB_CUDA(cudaEventSynchronize(ctx->ev_user[1]));
+  QMB_CUDA(cudaEventElapsedTime(ms, ctx->ev_user[0], ctx->ev_user[1]));
+  return QMB_OK;
+}
+
 extern "C" int qmb_ctx_flush_l2(qmb_ctx_t ctx) {
   if (!ctx) QMB_FAIL(QMB_ERR_ARG, "null context");
   QMB_CUDA(cudaSetDevice(ctx->device));
@@ -147,6 +169,8 @@ extern "C" int qmb_ctx_destroy(qmb_ctx_t ctx) {
   }
   for (int i = 0; i < 4; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < 2; ++i)
+    if (ctx->ev_user[i]) cudaEventDestroy(ctx->ev_user[i]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return QMB_OK;

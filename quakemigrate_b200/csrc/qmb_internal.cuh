@@ -93,6 +93,7 @@ struct qmb_ctx {
   int variant = QMB_DEFAULT_VARIANT;  // index into QMB_VARIANTS used for tables uploaded next
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_user[2] = {nullptr, nullptr};  // qmb_ctx_timer_start / stop
   int64_t launches = 0;
   int scan_fp32 = 0;      // detect scan operands: 0 automatic (16-bit fixed point when accurate enough), 1 float32, 2 16-bit
   int last_scan_q16 = 0;  // what the last detect scan actually used

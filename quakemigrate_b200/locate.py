@@ -109,26 +109,29 @@ def _finish(lut, spline_idx, gau_idx, gau_sigma, expect, cov, ijk):
             "peak_index": ijk}
 
 
-def calculate_location_device(coa_map_sum, lut, return_maps: bool = False) -> dict:
+def calculate_location_device(coa_map_sum, lut, return_maps: bool = False, engine_timer=None) -> dict:
     """
     ``_calculate_location`` (scan.py:696-733) on a :class:`~quakemigrate_b200.core.DeviceMap`
     holding the un-normalised marginal map: the map is normalised, smoothed and reduced on the
     device; only the peak (32 B), the 5^3 spline window, the 7^3 Gaussian-fit window and the 12
     covariance moments cross PCIe (< 5 KB per event; ``pcie_bytes`` in the result).
+    ``engine_timer`` (benchmarks): called once the last device operation of the event has
+    finished, before the host-side fits.
     """
+    # device work first (one stream, a few small read-backs), host algebra afterwards
     coa = coa_map_sum.normalise()                                   # scan.py:720-721
     ijk, _, _ = coa.peak()
     lo, hi = _window(coa.shape, ijk, 5)
     trim = coa.window(lo, hi)
-    spline_idx = spline_location_window(trim, lo, ijk)
-
     smoothed = coa.gaufilt()
     s_ijk, _, s_mean = smoothed.peak()
     lo7, hi7 = _window(coa.shape, s_ijk, 7)
     sub = smoothed.window(lo7, hi7)
-    gau_idx, gau_sigma = gaussian_fit_window(sub, lo7, s_ijk, s_mean)
-
     expect, cov = coa.covfit(lut.node_spacing, thresh=0.90)
+    if engine_timer is not None:
+        engine_timer()
+    spline_idx = spline_location_window(trim, lo, ijk)
+    gau_idx, gau_sigma = gaussian_fit_window(sub, lo7, s_ijk, s_mean)
     out = _finish(lut, spline_idx, gau_idx, gau_sigma, expect, cov, ijk)
     out["pcie_bytes"] = int(2 * 32 + trim.nbytes + sub.nbytes + 12 * 8 + 2 * 7 * 8)
     if return_maps:

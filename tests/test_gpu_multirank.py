@@ -52,6 +52,38 @@ for case, (grid, S, T, fsmp, lsmp, floor) in enumerate([((9, 6, 5), 6, 300, 5, 3
     np.testing.assert_allclose(got[0], want[0], rtol=1e-9)
     np.testing.assert_allclose(got[1], want[1], rtol=1e-5)
     lut.free()
+
+# a longer scan: 16-bit rows with the cross-rank verification of the node sums, spot-checked
+# against the fused oracle; then adversarial rows that must make EVERY rank fall back together
+cfg = syn.CONFIGS["cfg2"].scaled(grid=(30, 24, 14), n_samples=4200, n_rows=12, name="mr")
+prob = syn.make_problem(cfg)
+slab, off, n_glob = shard_traveltimes(prob.traveltimes, world, rank)
+lut = eng.upload_lut(slab, node_offset=off, n_nodes_global=n_glob)
+dev, onsets = eng.onsets_from_waveforms(prob.waveforms, prob.row_channels, prob.nsta, prob.nlta,
+                                        position=cfg.position, return_onsets=True)
+eng.detect_device(lut, dev, prob.fsmp, prob.lsmp, cfg.n_rows)
+info = eng.last_scan_info
+got = eng.detect_fetch(cfg.n_samples)
+assert info["operand_bytes"] == 2 and info["fell_back_fp32"] == 0 and info["check_max_rel_err"] <= 2e-6, info
+assert info["host_syncs_in_timed_region"] == 0
+want = O.detect_fused(onsets, prob.traveltimes, prob.fsmp, prob.lsmp, cfg.n_rows, threads=2)
+assert np.array_equal(got[2], want[2]), f"sharded 16-bit scan: argmax differs on rank {{rank}}"
+np.testing.assert_allclose(got[0], want[0], rtol=1e-9)
+np.testing.assert_allclose(got[1], want[1], rtol=1e-5)
+
+lo, hi = np.log(0.4), np.log(50.0)
+step = (hi - lo) / 65535.0
+t = np.arange(onsets.shape[1])
+adv = np.stack([np.exp(lo + (12000 + 11 * s + t // 3 + 0.499) * step) for s in range(cfg.n_rows)])
+adv[:, 5] = 0.4
+adv[:, 9] = 50.0
+got = eng.detect(lut, adv, prob.fsmp, prob.lsmp, cfg.n_rows)
+info = eng.last_scan_info
+assert info["fell_back_fp32"] == 1 and info["operand_bytes"] == 4, info
+want = O.detect_fused(adv, prob.traveltimes, prob.fsmp, prob.lsmp, cfg.n_rows, threads=2)
+assert np.array_equal(got[2], want[2])
+np.testing.assert_allclose(got[1], want[1], rtol=1e-5)
+lut.free()
 eng.close()
 print("rank", rank, "ok")
 """

@@ -44,24 +44,98 @@ def test_both_operand_formats_meet_the_contract(precision, bpg, seed):
     np.testing.assert_allclose(got[1], want[1], rtol=1e-5 if precision == "fp32" else 1e-4)
 
 
+def _run_info(precision, onsets, tau, fsmp, lsmp, avail):
+    from quakemigrate_b200.core import Engine
+    with Engine(0, precision=precision) as eng:
+        lut = eng.upload_lut(tau)
+        got = eng.detect(lut, onsets, fsmp, lsmp, avail)
+        info = eng.last_scan_info
+        lut.free()
+    return got, info
+
+
 def test_automatic_choice():
-    """auto = 16-bit rows at realistic sizes, float32 rows where the node sum could not average the
-    quantisation noise down (tiny grids; `available` far below the row count)."""
+    """auto = float32 rows for short scans (the verification windows would cost more than the 16-bit
+    rows save), 16-bit rows otherwise -- and then every call VERIFIES the node sums of the 16-bit
+    scan against float32 re-scans of 1-2 windows and redoes the scan in float32 when they differ by
+    more than 2e-6: max_norm_coa is inside 1e-5 whatever path was taken."""
     small = syn.random_problem(1, (3, 2, 2), 24, 300, 10, 60)
-    got, used = _run("auto", small[0], small[1], 10, 60, 24)
-    assert used == 4
+    got, info = _run_info("auto", small[0], small[1], 10, 60, 24)
+    assert info["operand_bytes"] == 4 and info["check_windows"] == 0
     want = O.detect_fused(small[0], small[1], 10, 60, 24, threads=2)
     assert np.array_equal(got[2], want[2])
     np.testing.assert_allclose(got[1], want[1], rtol=1e-5)
-    big = syn.random_problem(2, (40, 40, 30), 16, 400, 10, 60)
-    got, used = _run("auto", big[0], big[1], 10, 60, 16)
-    assert used == 2
+
+    big = syn.random_problem(2, (40, 40, 30), 16, 2400, 10, 60)
+    got, info = _run_info("auto", big[0], big[1], 10, 60, 16)
+    assert info["operand_bytes"] == 2 and info["fell_back_fp32"] == 0
+    assert info["check_windows"] >= 1 and info["check_samples"] >= 200
+    assert info["check_max_rel_err"] <= 2e-6
+    assert info["host_syncs_in_timed_region"] == 0
     want = O.detect_fused(big[0], big[1], 10, 60, 16, threads=8)
     assert np.array_equal(got[2], want[2])
     np.testing.assert_allclose(got[0], want[0], rtol=1e-9)
     np.testing.assert_allclose(got[1], want[1], rtol=1e-5)
-    got, used = _run("auto", big[0], big[1], 10, 60, 1)  # available = 1: no division of the error
-    assert used == 4
+
+    # available = 1: the quantisation error of a stack is not divided by the row count any more;
+    # the check sees it and the result comes from float32 rows
+    got, info = _run_info("auto", big[0], big[1], 10, 60, 1)
+    want = O.detect_fused(big[0], big[1], 10, 60, 1, threads=8)
+    assert np.array_equal(got[2], want[2])
+    np.testing.assert_allclose(got[1], want[1], rtol=1e-5)
+    assert info["operand_bytes"] == 4 or info["check_max_rel_err"] <= 2e-6
+
+
+def _adversarial_rows(S, P, kind, rng):
+    """Linear onsets whose LOG values sit half a quantisation step off the 16-bit grid, so that the
+    rounding residuals of all rows and all nodes have the same sign (the case a sqrt(N) averaging
+    argument gets wrong).  Two samples per row pin the common range [log 0.4, log 50]."""
+    lo, hi = np.log(0.4), np.log(50.0)
+    step = (hi - lo) / 65535.0
+    t = np.arange(P)
+    rows = np.empty((S, P))
+    for s in range(S):
+        if kind == "constant":
+            level = np.full(P, 20000 + 37 * s)
+        elif kind == "ramp":          # constant plus a slow ramp: a few thousand distinct levels
+            level = 12000 + 11 * s + t // 3
+        else:                          # "steps": few distinct values
+            level = 15000 + 1000 * ((t // 50 + s) % 4)
+        rows[s] = np.exp(lo + (level + 0.5 - 1e-3) * step)
+        rows[s, rng.integers(0, P)] = 0.4
+        rows[s, rng.integers(0, P)] = 50.0
+    return rows
+
+
+@pytest.mark.parametrize("kind", ["constant", "ramp", "steps"])
+@pytest.mark.parametrize("few_tau", [False, True])
+def test_correlated_quantisation_residuals_are_caught(kind, few_tau):
+    """Adversarial inputs for the 16-bit node sum: every residual is ~ +step/2,
+    so the quantised node sum is off by S * step / (2 available) ~ 3.7e-5 relative -- outside the
+    bar.  The automatic mode must notice (check_max_rel_err) and deliver 1e-5 anyway; arg-max and
+    max_coa stay exact in either format."""
+    rng = np.random.default_rng(7)
+    grid, S, T, fsmp, lsmp = (20, 18, 10), 8, 2500, 10, 80
+    P = fsmp + T + lsmp
+    onsets = _adversarial_rows(S, P, kind, rng)
+    if few_tau:
+        tau = rng.integers(0, 3, size=grid + (S,), dtype=np.int32) * 20
+    else:
+        _, tau = syn.random_problem(5, grid, S, T, fsmp, lsmp)
+    want = O.detect_fused(onsets, tau, fsmp, lsmp, S, threads=8)
+    got, info = _run_info("auto", onsets, tau, fsmp, lsmp, S)
+    assert np.array_equal(got[2], want[2])
+    np.testing.assert_allclose(got[0], want[0], rtol=1e-9)
+    np.testing.assert_allclose(got[1], want[1], rtol=1e-5)
+    assert info["check_windows"] >= 1
+    assert info["fell_back_fp32"] == 1 and info["operand_bytes"] == 4 and info["check_max_rel_err"] > 2e-6
+    # forced 16-bit rows: same indices and max_coa, and the reported check error IS the error
+    got_q, info_q = _run_info("q16", onsets, tau, fsmp, lsmp, S)
+    assert np.array_equal(got_q[2], want[2])
+    np.testing.assert_allclose(got_q[0], want[0], rtol=1e-9)
+    err = float(np.max(np.abs(got_q[1] - want[1]) / want[1]))
+    assert info_q["operand_bytes"] == 2 and info_q["fell_back_fp32"] == 0
+    assert err > 1e-5 and 0.3 * err <= info_q["check_max_rel_err"] <= 3.0 * err
 
 
 def test_formats_agree_with_each_other_on_a_planted_event():
