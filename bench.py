@@ -64,6 +64,9 @@ def parse_args():
     ap.add_argument("--samples", type=int, default=0, help="override n_samples (debug)")
     ap.add_argument("--precision", default=None, choices=["auto", "q16", "fp32"],
                     help="operand format of the scan's gathers (library default: auto -> verified q16)")
+    ap.add_argument("--qgroup", type=int, default=None, choices=[1, 2, 4, 8],
+                    help="rows per carry-free group of the fixed-point scan (1: 16-bit rows ... 8: 13-bit rows); "
+                         "default: the library's")
     ap.add_argument("--no-cpu-baseline", action="store_true",
                     help="skip the reference-C parity windows / CPU baseline (profiling runs)")
     ap.add_argument("--pre-only", action="store_true",
@@ -363,7 +366,8 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
     N_global, T, S = cfg.n_nodes, cfg.n_samples, cfg.n_rows
     P = prob.n_total
 
-    eng = Engine(local_rank, variant=args.variant if args.variant >= 0 else None, precision=args.precision)
+    eng = Engine(local_rank, variant=args.variant if args.variant >= 0 else None, precision=args.precision,
+                 qgroup=args.qgroup)
     if args.pre_only:
         print(json.dumps(preprocess_stage(eng, base, prob, args, *measured_peak_hbm())), flush=True)
         eng.close()
@@ -461,8 +465,8 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
             "cache": "L2 flushed (256 MiB memset) before every timed step",
             "nodes_per_tile": info["nodes_per_tile"], "max_tile_span": info["max_tile_span"],
             "variant": info["variant"], "duplicate_fraction": round(info["duplicate_fraction"], 4),
-            "scan_operands": "16-bit fixed point (2 per LDS.32), node sums verified against float32 windows"
-                             if bpg == 2 else "float32",
+            "scan_operands": f"{scan_info['operand_bits']}-bit fixed point (2 per LDS.32), node sums verified "
+                             "against float32 windows" if bpg == 2 else "float32",
             "timing": "sum of per-step CUDA-event times on the launching stream (scan + merge + exchange + "
                       "candidates + slow path + verification windows), max over ranks",
             "git": git_head(),
@@ -493,7 +497,8 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
         "wall_s_timed_region": wall,
         "slow_path_samples": slow,
         "tail_ms_per_step": tail_mean,
-        "scan": {"operand_bytes": scan_info["operand_bytes"], "fell_back_fp32": scan_info["fell_back_fp32"],
+        "scan": {"operand_bytes": scan_info["operand_bytes"], "operand_bits": scan_info["operand_bits"],
+                 "fell_back_fp32": scan_info["fell_back_fp32"],
                  "check_windows": scan_info["check_windows"], "check_samples": scan_info["check_samples"],
                  "check_max_rel_err": scan_info["check_max_rel_err"], "check_ms": scan_info["check_ms"],
                  "two_candidate_samples": scan_info["two_candidate_samples"],
@@ -536,7 +541,8 @@ def run_locate(args, rank: int, world: int, local_rank: int, dist):
     prob = syn.make_problem(cfg, with_waveforms=True)
     N, T, S = cfg.n_nodes, cfg.n_samples, cfg.n_rows
     mw = 2.0  # QuakeScan.marginal_window default (scan.py:236)
-    eng = Engine(local_rank, variant=args.variant if args.variant >= 0 else None, precision=args.precision)
+    eng = Engine(local_rank, variant=args.variant if args.variant >= 0 else None, precision=args.precision,
+                 qgroup=args.qgroup)
     lut = eng.upload_lut(prob.traveltimes)
     dev_on, onsets_lin = eng.onsets_from_waveforms(prob.waveforms, prob.row_channels, prob.nsta, prob.nlta,
                                                    position=cfg.position, return_onsets=True)
@@ -544,7 +550,7 @@ def run_locate(args, rank: int, world: int, local_rank: int, dist):
     info = lut.info()
 
     def event(dev, stamps=None):
-        """The device part of one event; returns (result dict, location)."""
+        """One located event; the CUDA-event timer (started by the caller) stops after the last device op."""
         ms = eng.detect_device(lut, dev, prob.fsmp, prob.lsmp, S)
         mx, nm, ix = eng.detect_fetch(T)
         i0, i1, imax = marginal_window_indices(mx, mw, cfg.sampling_rate)
@@ -554,7 +560,12 @@ def run_locate(args, rank: int, world: int, local_rank: int, dist):
         if stamps is not None:
             eng.sync(); stamps.append(time.perf_counter())
         box = {}
-        loc = calculate_location_device(dmap, grid, engine_timer=lambda: box.setdefault("ms", eng.timer_stop()))
+
+        def device_done():
+            box["ms"] = eng.timer_stop()
+            if stamps is not None:
+                stamps.append(time.perf_counter())
+        loc = calculate_location_device(dmap, grid, engine_timer=device_done)
         dmap.free()
         return {"scan": ms, "window": (i0, i1), "peak_sample": imax, "idx": ix[imax], "device_ms": box["ms"]}, loc
 
@@ -567,21 +578,26 @@ def run_locate(args, rank: int, world: int, local_rank: int, dist):
         dist.barrier()
     sampler.start()
     launches0 = eng.launch_count
-    dev_ms, scan_ms, stage = [], [], []
+    dev_ms, scan_ms = [], []
     for _ in range(args.steps):
         eng.flush_l2()
-        stamps = [time.perf_counter()]
         eng.timer_start()
-        out, loc = event(dev_on, stamps)
-        stamps.append(time.perf_counter())
+        out, loc = event(dev_on)
         dev_ms.append(out["device_ms"])
         scan_ms.append(out["scan"]["scan_ms"])
-        stage.append(np.diff(stamps))
     eng.sync()
     if world > 1:
         dist.barrier()
     launches = eng.launch_count - launches0
     clocks = sampler.stop()
+    # stage breakdown (wall clock between device synchronisations; outside the timed region)
+    stage = []
+    for _ in range(3):
+        stamps = [time.perf_counter()]
+        eng.timer_start()
+        event(dev_on, stamps)
+        stamps.append(time.perf_counter())
+        stage.append(np.diff(stamps))
 
     # ---- e2e: host onsets in, location out (H2D of the onsets, host fits included) ---------------
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
@@ -608,7 +624,7 @@ def run_locate(args, rank: int, world: int, local_rank: int, dist):
         dev_total_ms, e2e_sec, scan_mean = [float(x) for x in t]
     ms_per_step = dev_total_ms / args.steps
     value = world * N * T / (ms_per_step * 1e-3)
-    st = np.median(np.array(stage), axis=0) * 1e3  # span pass, window pass, map stage + host fits (ms, wall)
+    st = np.median(np.array(stage), axis=0) * 1e3  # span pass, window pass, device map stage, host fits (ms, wall)
     i0, i1 = out["window"]
     Wn = i1 - i0
 
@@ -653,7 +669,9 @@ def run_locate(args, rank: int, world: int, local_rank: int, dist):
                           "frac": ga * bpg / (smem_peak * 4), "sm_mhz_used": sm_mhz},
         },
         "stages": {
-            "span_pass_ms": float(st[0]), "window_pass_ms": float(st[1]), "map_stage_and_fits_ms": float(st[2]),
+            "span_pass_ms": float(st[0]), "window_pass_ms": float(st[1]), "device_map_stage_ms": float(st[2]),
+            "host_fits_ms": float(st[3]),
+            "note": "wall clock between device synchronisations, measured outside the timed region",
             "window_pass": {
                 "what": "k_scan MODE 1 on float32 rows: exp(stack/available) summed over the window per node",
                 "roofline": {"bound": "hbm", "achieved": win_hbm / (st[1] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",

@@ -103,6 +103,13 @@ int qmb_ctx_set_variant(qmb_ctx_t ctx, int nodes_per_warp);
  * with QMB_SCAN_PRECISION=fp32|q16.  qmb_ctx_last_scan_bytes_per_gather reports what the last
  * detect scan moved per gathered operand (2 or 4 bytes). */
 int qmb_ctx_set_scan_precision(qmb_ctx_t ctx, int mode);
+/* Fixed-point rows of the detect scan are quantised to 16 - log2(group) bits so that `group` rows
+ * (1, 2, 4 or 8) can be added word-wise before the two 16-bit halves are separated: 1 = full 16-bit
+ * rows, two instructions per shared-memory word; 4 = 14-bit rows, one.  The candidate band is
+ * S * q_step (q_step doubles per bit dropped); results do not depend on it (float64 decision among
+ * the candidates, verified node sums).  Applies to onsets and tables prepared afterwards; also
+ * QMB_SCAN_QGROUP. */
+int qmb_ctx_set_scan_qgroup(qmb_ctx_t ctx, int group);
 int qmb_ctx_last_scan_bytes_per_gather(qmb_ctx_t ctx, int *bytes);
 /* What the last detect scan did.  The 16-bit scan is VERIFIED per call: after the scan, 1-2 windows
  * of 248 samples are re-scanned over all local nodes with float32 rows and the per-sample node sums
@@ -122,7 +129,7 @@ typedef struct {
                                                  (merge, exchange, candidates, slow path, check), both,
                                                  and the check windows alone (part of tail_ms) */
   int32_t host_syncs_in_timed_region; /* cudaStreamSynchronize calls between the first and last event */
-  int32_t reserved;
+  int32_t operand_bits;               /* 32 (float32 rows) or the bits of the fixed-point rows (13..16) */
 } qmb_scan_info_t;
 int qmb_ctx_last_scan_info(qmb_ctx_t ctx, qmb_scan_info_t *info);
 /* number of launches of this library's own kernels since context creation */

@@ -54,7 +54,7 @@ class ScanInfo(ctypes.Structure):
                 ("slow_path_samples", c_int32), ("two_candidate_samples", c_int32),
                 ("scan_ms", ctypes.c_float), ("tail_ms", ctypes.c_float), ("total_ms", ctypes.c_float),
                 ("check_ms", ctypes.c_float), ("host_syncs_in_timed_region", c_int32),
-                ("reserved", c_int32)]
+                ("operand_bits", c_int32)]
 
 
 class QmbError(RuntimeError):
@@ -83,6 +83,7 @@ SIGNATURES = {
     "qmb_ctx_sync": (ctypes.c_int, [c_void_p]),
     "qmb_ctx_set_variant": (ctypes.c_int, [c_void_p, ctypes.c_int]),
     "qmb_ctx_set_scan_precision": (ctypes.c_int, [c_void_p, ctypes.c_int]),
+    "qmb_ctx_set_scan_qgroup": (ctypes.c_int, [c_void_p, ctypes.c_int]),
     "qmb_ctx_last_scan_bytes_per_gather": (ctypes.c_int, [c_void_p, ctypes.POINTER(ctypes.c_int)]),
     "qmb_ctx_last_scan_info": (ctypes.c_int, [c_void_p, ctypes.POINTER(ScanInfo)]),
     "qmb_ctx_launch_count": (ctypes.c_int, [c_void_p, ctypes.POINTER(c_int64)]),

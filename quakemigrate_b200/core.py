@@ -276,7 +276,8 @@ class DeviceWaveforms:
 class Engine:
     """One GPU context: streams, scratch, optional NCCL communicator."""
 
-    def __init__(self, device: int = 0, variant: int | None = None, precision: str | None = None):
+    def __init__(self, device: int = 0, variant: int | None = None, precision: str | None = None,
+                 qgroup: int | None = None):
         self._lib = _lib.load()
         h = ctypes.c_void_p()
         _lib.check(self._lib.qmb_ctx_create(int(device), ctypes.byref(h)))
@@ -289,6 +290,9 @@ class Engine:
             _lib.check(self._lib.qmb_ctx_set_variant(self._h, int(variant)))
         if precision is not None:
             self.set_scan_precision(precision)
+        if qgroup is not None:
+            # rows per carry-free group of the fixed-point scan: 1 (16-bit rows), 2, 4, 8 (13-bit)
+            _lib.check(self._lib.qmb_ctx_set_scan_qgroup(self._h, int(qgroup)))
 
     # -- lifetime ---------------------------------------------------------------------------
     def __enter__(self):
@@ -340,7 +344,7 @@ class Engine:
         """
         inf = _lib.ScanInfo()
         _lib.check(self._lib.qmb_ctx_last_scan_info(self._h, ctypes.byref(inf)))
-        return {name: getattr(inf, name) for name, _ in inf._fields_ if name != "reserved"}
+        return {name: getattr(inf, name) for name, _ in inf._fields_}
 
     @property
     def launch_count(self) -> int:

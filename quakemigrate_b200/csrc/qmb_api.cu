@@ -55,6 +55,10 @@ extern "C" int qmb_ctx_create(int device, qmb_ctx_t *out) {
   for (int i = 0; i < 4; ++i) QMB_CUDA(cudaEventCreate(&ctx->ev[i]));
   if (const char *pr = getenv("QMB_SCAN_PRECISION"))
     ctx->scan_fp32 = strcmp(pr, "fp32") == 0 ? 1 : (strcmp(pr, "q16") == 0 ? 2 : 0);
+  if (const char *g = getenv("QMB_SCAN_QGROUP")) {
+    const int gi = atoi(g);
+    if (gi == 1 || gi == 2 || gi == 4 || gi == 8) ctx->scan_qgroup = gi;
+  }
   const char *v = getenv("QMB_VARIANT");
   if (v && atoi(v) >= 0 && atoi(v) < QMB_N_VARIANTS) ctx->variant = atoi(v);
   *out = ctx;
@@ -73,6 +77,14 @@ extern "C" int qmb_ctx_set_scan_precision(qmb_ctx_t ctx, int mode) {
   if (!ctx) QMB_FAIL(QMB_ERR_ARG, "null context");
   if (mode < 0 || mode > 2) QMB_FAIL(QMB_ERR_ARG, "precision mode must be 0 (auto), 1 (float32) or 2 (16-bit)");
   ctx->scan_fp32 = mode;
+  return QMB_OK;
+}
+
+extern "C" int qmb_ctx_set_scan_qgroup(qmb_ctx_t ctx, int group) {
+  if (!ctx) QMB_FAIL(QMB_ERR_ARG, "null context");
+  if (group <= 0) group = QMB_DEFAULT_QGROUP;
+  if (group != 1 && group != 2 && group != 4 && group != 8) QMB_FAIL(QMB_ERR_ARG, "row group must be 1, 2, 4 or 8");
+  ctx->scan_qgroup = group;
   return QMB_OK;
 }
 
@@ -408,7 +420,7 @@ extern "C" int qmb_lut_free(qmb_lut_t L) {
   if (!L) return QMB_OK;
   cudaSetDevice(L->device);
   L->tau16.release(); L->tmin.release(); L->span.release(); L->nodeidx.release();
-  L->boxes.release(); L->slotmap.release(); L->tauq16.release();
+  L->boxes.release(); L->slotmap.release(); L->tauq16.release(); L->tauq32.release();
   delete L;
   return QMB_OK;
 }

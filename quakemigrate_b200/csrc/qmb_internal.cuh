@@ -58,6 +58,7 @@ constexpr QmbVariant QMB_VARIANTS[QMB_N_VARIANTS] = {
 constexpr int QMB_DEFAULT_VARIANT = 7;  // measured best on B200 (scripts/sweep_variants.sh)
 constexpr int QMB_DEFAULT_CHUNK_ROWS = 16;  // onset rows (station x phase) staged per pipeline stage
 constexpr int QMB_SMEM_BUDGET = 227 * 1024;
+constexpr int QMB_DEFAULT_QGROUP = 4;  // 14-bit rows, four rows per carry-free group
 
 // ---------------------------------------------------------------------------------------------
 // device buffer helper (RAII-free; owned by the structs below)
@@ -95,6 +96,7 @@ struct qmb_ctx {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_user[2] = {nullptr, nullptr};  // qmb_ctx_timer_start / stop
   int64_t launches = 0;
+  int scan_qgroup = QMB_DEFAULT_QGROUP;  // rows per carry-free group of the fixed-point scan (1, 2, 4, 8)
   int scan_fp32 = 0;      // detect scan operands: 0 automatic (16-bit fixed point when accurate enough), 1 float32, 2 16-bit
   int last_scan_q16 = 0;  // what the last detect scan actually used
 
@@ -163,6 +165,10 @@ struct qmb_lut {
   // "even" one); RSq = elements per staged stream
   DevBuf<uint16_t> tauq16;  // [n_tiles][Spad][NB]
   int32_t RSq = 0;
+  // packed scan (groups of qG rows): BYTE offset of the pair inside the stage, row position included,
+  // laid out [n_tiles][Spad / qG][NB][qG] so that one vector load fetches a node's offsets of a group
+  DevBuf<uint32_t> tauq32;
+  int32_t qG = 1;
 };
 
 struct qmb_ttgrids {  // every (station, phase) travel-time grid, float64 seconds, on the device
@@ -192,6 +198,7 @@ struct qmb_onsets {
   DevBuf<uint16_t> q16;
   DevBuf<double> qrange;  // [S][2] min / max of each row
   int64_t qstride = 0, qfront = 0;
+  int32_t qG = 1, qbits = 16, qlevels = 65535;  // rows per carry-free group <-> bits per sample
   double qmin = 0.0, qstep = 0.0;  // qstep == 0: no quantised copy (e.g. rows of the T1 migrate())
 };
 

@@ -135,6 +135,21 @@ __global__ void __launch_bounds__(256) k_lut_tauq(const uint16_t *tau16, uint16_
   tauq16[i] = (uint16_t)((t >> 1) + (t & 1u) * (unsigned)half_words);
 }
 
+// byte offsets for the packed scan: [tile][row group][slot][G]; value = position of the row inside
+// its pipeline stage + the pair's word inside the row (the odd stream sits RSq * 2 bytes further)
+__global__ void __launch_bounds__(256) k_lut_tauq32(const uint16_t *tau16, uint32_t *tauq32, size_t n, int Spad, int NB,
+                                                    int CR, int G, int RSq) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // index into tau16: (tile*Spad + s)*NB + slot
+  if (i >= n) return;
+  const unsigned t = tau16[i];
+  const int slot = (int)(i % NB);
+  const size_t js = i / NB;
+  const int s = (int)(js % Spad);
+  const size_t j = js / Spad;
+  const uint32_t off = (uint32_t)(s % CR) * (uint32_t)RSq * 4u + 4u * (t >> 1) + (t & 1u) * (uint32_t)RSq * 2u;
+  tauq32[((j * (size_t)(Spad / G) + (size_t)(s / G)) * NB + slot) * G + (s % G)] = off;
+}
+
 }  // namespace
 
 // Elements per staged 16-bit stream for this table: the widest window [tmin, tmin + span + TT + 1]
@@ -265,9 +280,21 @@ static int lut_build_variant(qmb_ctx *ctx, qmb_lut *L, const int32_t *d_raw, con
     k_lut_tauq<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(L->tau16.p, L->tauq16.p, n, L->RSq / 2);
     ctx->launches++;
     QMB_CUDA(cudaGetLastError());
+    L->qG = 1;
+    L->tauq32.release();
+    if (ctx->scan_qgroup > 1 && (L->chunk_rows % ctx->scan_qgroup) == 0 && L->v.NPW == 4) {
+      L->qG = ctx->scan_qgroup;
+      QMB_TRY(L->tauq32.ensure(n));
+      k_lut_tauq32<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(L->tau16.p, L->tauq32.p, n, L->Spad, L->NB,
+                                                                        L->chunk_rows, L->qG, L->RSq);
+      ctx->launches++;
+      QMB_CUDA(cudaGetLastError());
+    }
   } else {
     L->RSq = 0;
     L->tauq16.release();
+    L->tauq32.release();
+    L->qG = 1;
   }
   return QMB_OK;
 }

@@ -257,7 +257,8 @@ __global__ void __launch_bounds__(256) k_onset_range(const double *log64, long l
 // u(pos - qfront) in the even stream and u(pos - qfront + 1) in the odd stream.
 __global__ void __launch_bounds__(256) k_onset_quantise(const double *log64, long long stride, long long front,
                                                         long long P, uint16_t *q16, long long qstride,
-                                                        long long qfront, double qmin, double inv_step) {
+                                                        long long qfront, double qmin, double inv_step,
+                                                        double top) {
   const int s = blockIdx.y;
   const long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (pos >= qstride) return;
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(256) k_onset_quantise(const double *log64, lon
   auto quant = [&](long long i) -> uint16_t {
     if (i < 0 || i >= P) return (uint16_t)0;
     const double u = rint((row[i] - qmin) * inv_step);
-    return (uint16_t)fmin(fmax(u, 0.0), 65535.0);
+    return (uint16_t)fmin(fmax(u, 0.0), top);
   };
   const long long i = pos - qfront;
   q16[((size_t)2 * s + 0) * qstride + pos] = quant(i);
@@ -309,14 +310,23 @@ int qmb_onsets_quantise(qmb_ctx *ctx, qmb_onsets *O) {
     if (range[2 * s + 1] > mx) mx = range[2 * s + 1];
   }
   if (!(mn <= mx) || !isfinite(mn) || !isfinite(mx)) return QMB_OK;  // NaN/inf rows: float32 scan only
+  // rows per carry-free group of the packed scan <-> bits per sample (G rows of (16 - log2 G)-bit
+  // values add up inside 16 bits); rows beyond S up to a multiple of 8 are zero (they pad a group)
+  O->qG = ctx->scan_qgroup;
+  O->qbits = O->qG == 8 ? 13 : (O->qG == 4 ? 14 : (O->qG == 2 ? 15 : 16));
+  O->qlevels = (1 << O->qbits) - 1;
   O->qmin = mn;
-  O->qstep = mx > mn ? (mx - mn) / 65535.0 : 1.0;
+  O->qstep = mx > mn ? (mx - mn) / (double)O->qlevels : 1.0;
   O->qfront = QMB_ONSET_QFRONT;
   O->qstride = ((O->qfront + O->P + QMB_ONSET_TAIL + 7) / 8) * 8;
-  QMB_TRY(O->q16.ensure((size_t)2 * O->S * O->qstride));
+  const size_t S8 = ((size_t)O->S + 7) & ~(size_t)7;
+  QMB_TRY(O->q16.ensure((size_t)2 * S8 * O->qstride));
+  if (S8 > (size_t)O->S)
+    QMB_CUDA(cudaMemsetAsync(O->q16.p + (size_t)2 * O->S * O->qstride, 0,
+                             (size_t)2 * (S8 - O->S) * O->qstride * sizeof(uint16_t), ctx->stream));
   dim3 grid((unsigned)((O->qstride + 255) / 256), (unsigned)O->S);
   k_onset_quantise<<<grid, 256, 0, ctx->stream>>>(O->log64.p, O->stride, O->front, O->P, O->q16.p, O->qstride,
-                                                  O->qfront, O->qmin, 1.0 / O->qstep);
+                                                  O->qfront, O->qmin, 1.0 / O->qstep, (double)O->qlevels);
   ctx->launches++;
   QMB_CUDA(cudaGetLastError());
   return QMB_OK;

@@ -38,6 +38,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "qmb_internal.cuh"
 
@@ -105,8 +106,13 @@ struct ScanParams {
   // 1 and 65536 as kernel parameters: multiplying by them keeps the word / upper-half accumulation
   // on the fma pipe (IMAD, IMAD.HI) -- the compiler cannot fold a multiplier it does not know --
   // while shifts and adds would all land on the alu pipe, which is the one that saturates
-  uint32_t q_one, q_64k;
+  uint32_t q_one, q_64k, q_m64k;  // q_m64k = -65536
   int q_form;  // 0: IADD3 + LEA.HI (alu)  1: IMAD word sums  2: 1 + IMAD.HI for odd words  3: IMAD / IADD3 alternating
+  // MODE 8+ (carry-free packed lanes): rows quantised to 16 - log2(G) bits, G rows are added word-wise
+  // before the halves are split; tauq32 = byte offsets [tile][row group][slot][G]; Sg = S rounded up to G
+  const uint32_t *tauq32;
+  int Sg;
+  float qa, qb;  // exp2 argument of a stack: qa * sum(u) + qb = (qc0 + qstep * sum(u)) * scale
   long long row_stride;  // elements
   long long t_origin;    // index within a row of (tau = 0, sample t' = 0); multiple of 4
   int S, n_chunks;       // n_chunks = stages per node tile (rows / CR)
@@ -147,7 +153,7 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
   // stage layout: [16 rows x RS floats][16 x NB uint16 tau][NB uint32 node index]
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t rows_bytes = (uint32_t)CR * p.RS * 4u;
-  constexpr uint32_t tau_bytes = (uint32_t)CR * NB * 2u;
+  constexpr uint32_t tau_bytes = (uint32_t)CR * NB * (MODE >= 8 ? 4u : 2u);
   const uint32_t bar_base = smem_base + (uint32_t)p.n_stages * p.stage_bytes;  // full[], then empty[]
 
   if (threadIdx.x == 0) {
@@ -173,7 +179,7 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
       for (int j = tile0; j < tile1; ++j) {
         for (int c = 0; c < p.n_chunks; ++c) {
           const int s = c * CR + lane;
-          const bool act = lane < CR && s < p.S;
+          const bool act = lane < CR && s < (MODE >= 8 ? p.Sg : p.S);  // MODE 8+: zero rows pad a row group
           // metadata loads are issued before the wait so their latency overlaps it
           int tmin = 0, len = 0;
           if (act) {
@@ -203,9 +209,12 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
             bulk_g2s(stage + (uint32_t)lane * p.RS * 4u, p.on32 + (size_t)s * p.row_stride + tbase + tmin,
                      bytes, full);
           }
-          if (lane == 0)
-            bulk_g2s(stage + rows_bytes, p.tau16 + ((size_t)j * p.Spad + (size_t)c * CR) * NB,
-                     tau_bytes, full);
+          if (lane == 0) {
+            if constexpr (MODE >= 8)
+              bulk_g2s(stage + rows_bytes, p.tauq32 + ((size_t)j * p.Spad + (size_t)c * CR) * NB, tau_bytes, full);
+            else
+              bulk_g2s(stage + rows_bytes, p.tau16 + ((size_t)j * p.Spad + (size_t)c * CR) * NB, tau_bytes, full);
+          }
           if (lane == 1 && c == 0)
             bulk_g2s(stage + rows_bytes + tau_bytes, p.nodeidx + (size_t)j * NB, NB * 4u, full);
           if (++st == p.n_stages) { st = 0; ph ^= 1u; }
@@ -232,7 +241,172 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
       sum[k] = 0.0;
     }
 
-    if constexpr (MODE >= 4) {
+    if constexpr (MODE >= 8) {
+      // ---- carry-free packed lanes -------------------------------------------------------------
+      // Rows are quantised to 16 - log2(G) bits, so the two 16-bit halves of G words can be added
+      // as ONE 32-bit integer without a carry crossing from the lower into the upper half:
+      //   t = w_0 + ... + w_{G-1}   (IADD / IADD3: half an instruction per word)
+      //   Hs += t >> 16 ; A += t    (once per G rows)
+      // against two instructions per word for full 16-bit rows.  Offsets are byte offsets inside
+      // the stage (row position included), G of them per (row group, node) in one vector load.
+      constexpr int G = 1 << (MODE - 7);
+      constexpr int H = G / 2;  // row pairs per group
+      static_assert(NPW == 4 && (K % 2) == 0 && (CR % G) == 0 && G >= 2 && G <= 8, "packed scan geometry");
+      constexpr int KW = K / 2;
+      constexpr uint32_t OG = (uint32_t)NB * G * 4u;  // offset bytes per row group
+      int M1[K], M2[K], M3[K];  // running top-3 of the integer stacks (sum of the quantised rows)
+#pragma unroll
+      for (int k = 0; k < K; ++k) M1[k] = M2[k] = M3[k] = -1;
+      for (int j = tile0; j < tile1; ++j) {
+        uint32_t A[NPW][KW], Hs[NPW][KW];
+#pragma unroll
+        for (int q = 0; q < NPW; ++q)
+#pragma unroll
+          for (int k = 0; k < KW; ++k) A[q][k] = Hs[q][k] = 0u;
+        uint32_t nidx[NPW];
+        for (int c = 0; c < p.n_chunks; ++c) {
+          const uint32_t full = bar_base + 8u * st, empty = bar_base + 8u * (p.n_stages + st);
+          const uint32_t stage = smem_base + (uint32_t)st * p.stage_bytes;
+          mbar_wait(full, ph);
+          if (c == 0) {
+            const uint32_t ia = stage + rows_bytes + tau_bytes + (uint32_t)(warp * NPW) * 4u;
+#pragma unroll
+            for (int q = 0; q < NPW; ++q)
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(nidx[q]) : "r"(ia + 4u * q));
+          }
+          const int ngroups = min(CR, p.Sg - c * CR) / G;
+          const uint32_t lane_base = stage + (uint32_t)lane * 4u;
+          const uint32_t oa = stage + rows_bytes + (uint32_t)(warp * NPW) * (G * 4u);
+          auto lds_off = [&](uint32_t addr, uint32_t (&o)[G]) {
+            if constexpr (G == 2) {
+              asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(o[0]), "=r"(o[1]) : "r"(addr));
+            } else {
+#pragma unroll
+              for (int i = 0; i < G; i += 4)
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(o[i]), "=r"(o[i + 1]), "=r"(o[i + 2]), "=r"(o[i + 3])
+                             : "r"(addr + 4u * i));
+            }
+          };
+          auto load_pair = [&](const uint32_t (&o)[G], int h, uint32_t (&vv)[2][KW]) {
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+              const uint32_t a = lane_base + o[2 * h + rr];
+#pragma unroll
+              for (int k = 0; k < KW; ++k)
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(vv[rr][k]) : "r"(a + 128u * k));
+            }
+          };
+          uint32_t off[2][G];
+          uint32_t v[2][2][KW];
+          uint32_t t[KW];
+          lds_off(oa, off[0]);
+          lds_off(oa + G * 4u, off[1]);
+          load_pair(off[0], 0, v[0]);
+          for (int g = 0; g < ngroups; ++g) {
+            // the prefetches that reach into the next group are issued unconditionally (no second
+            // code path, no register shuffling at the loop edge): after the last group of the stage
+            // they re-read this group, and their results are dropped
+            const uint32_t og = oa + (uint32_t)g * OG;
+            const uint32_t ogn = g + 1 < ngroups ? og + OG : og;
+#pragma unroll
+            for (int q = 0; q < NPW; ++q) {
+#pragma unroll
+              for (int h = 0; h < H; ++h) {
+                const int n = q * H + h;
+                // loads of the next unit first, then the adds of this one
+                if (h + 1 < H) load_pair(off[q & 1], h + 1, v[(n + 1) & 1]);
+                else if (q + 1 < NPW) load_pair(off[(q + 1) & 1], 0, v[(n + 1) & 1]);
+                else load_pair(off[0], 0, v[(n + 1) & 1]);
+                uint32_t (&vv)[2][KW] = v[n & 1];
+#pragma unroll
+                for (int k = 0; k < KW; ++k) {
+                  if (h == 0) t[k] = vv[0][k] + vv[1][k];
+                  else t[k] = t[k] + vv[0][k] + vv[1][k];
+                }
+                if (h == H - 1) {
+#pragma unroll
+                  for (int k = 0; k < KW; ++k) {
+                    Hs[q][k] += t[k] >> 16;
+                    A[q][k] = t[k] * p.q_one + A[q][k];
+                  }
+                  // this node's offsets are consumed: fetch those of the node two units ahead
+                  if (q + 2 < NPW) lds_off(og + (uint32_t)(q + 2) * (G * 4u), off[q & 1]);
+                  else lds_off(ogn + (uint32_t)(q + 2 - NPW) * (G * 4u), off[q & 1]);
+                }
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty);
+          if (++st == p.n_stages) { st = 0; ph ^= 1u; }
+        }
+        // ---- per-tile epilogue: slot k = 2 kk + h <-> sample 64 kk + 2 lane + h ---------------
+        // The running top-3 lives on the exact integer stacks (one float conversion per survivor
+        // at the end of the item).  A stack that does not beat the current third value cannot
+        // change the state, and after a few hundred tiles that is the rule: the four nodes of the
+        // warp are folded into their maximum and the insertion is skipped unless some lane needs it
+        // (warp vote).  Padding slots (warp-uniform, rare) take part with stack -1 = never.
+        auto epilogue = [&](auto haspad_tag) {
+          constexpr bool HASPAD = decltype(haspad_tag)::value;
+#pragma unroll
+          for (int kk = 0; kk < KW; ++kk) {
+            int u[2][NPW];
+            float e0 = 0.f, e1 = 0.f;
+#pragma unroll
+            for (int q = 0; q < NPW; ++q) {
+              const bool pad = HASPAD && nidx[q] == 0xFFFFFFFFu;
+              const uint32_t hi = Hs[q][kk], lo = hi * p.q_m64k + A[q][kk];
+              const float x0 = ex2_approx(fmaf((float)lo, p.qa, p.qb));  // exp(stack / available)
+              const float x1 = ex2_approx(fmaf((float)hi, p.qa, p.qb));
+              e0 += pad ? 0.f : x0;
+              e1 += pad ? 0.f : x1;
+              u[0][q] = pad ? -1 : (int)lo;
+              u[1][q] = pad ? -1 : (int)hi;
+            }
+            sum[2 * kk] += (double)e0;
+            sum[2 * kk + 1] += (double)e1;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int k = 2 * kk + h;
+              const int top = max(max(u[h][0], u[h][1]), max(u[h][2], u[h][3]));
+              if (__any_sync(0xffffffffu, top > M3[k])) {
+#pragma unroll
+                for (int q = 0; q < NPW; ++q) {
+                  const int v1 = u[h][q];
+                  const bool g1 = v1 > M1[k];
+                  const bool g2 = v1 > M2[k];
+                  M3[k] = g2 ? M2[k] : max(M3[k], v1);
+                  M2[k] = g1 ? M1[k] : (g2 ? v1 : M2[k]);
+                  i2[k] = g1 ? i1[k] : (g2 ? nidx[q] : i2[k]);
+                  M1[k] = g1 ? v1 : M1[k];
+                  i1[k] = g1 ? nidx[q] : i1[k];
+                }
+              }
+            }
+          }
+        };
+        // padding slots are warp-uniform and rare (ragged grid edges): a separate instance
+        if (nidx[0] == 0xFFFFFFFFu || nidx[1] == 0xFFFFFFFFu || nidx[2] == 0xFFFFFFFFu || nidx[3] == 0xFFFFFFFFu)
+          epilogue(std::true_type{});
+        else
+          epilogue(std::false_type{});
+      }
+      // ---- item done: publish (pairs of neighbouring samples -> 8 / 16-byte stores) -----------
+      const size_t base = ((size_t)r * W + warp) * p.Tpad + (size_t)tt * TT + 2u * lane;
+      auto tofloat = [&](int v) { return v < 0 ? NEG_INF : fmaf((float)v, p.qstep, p.qc0); };
+#pragma unroll
+      for (int kk = 0; kk < KW; ++kk) {
+        const size_t o = base + 64u * kk;
+        *reinterpret_cast<float2 *>(p.pm1 + o) = make_float2(tofloat(M1[2 * kk]), tofloat(M1[2 * kk + 1]));
+        *reinterpret_cast<float2 *>(p.pm2 + o) = make_float2(tofloat(M2[2 * kk]), tofloat(M2[2 * kk + 1]));
+        *reinterpret_cast<float2 *>(p.pm3 + o) = make_float2(tofloat(M3[2 * kk]), tofloat(M3[2 * kk + 1]));
+        *reinterpret_cast<uint2 *>(p.pi1 + o) = make_uint2(i1[2 * kk], i1[2 * kk + 1]);
+        *reinterpret_cast<uint2 *>(p.pi2 + o) = make_uint2(i2[2 * kk], i2[2 * kk + 1]);
+        *reinterpret_cast<double2 *>(p.psum + o) = make_double2(sum[2 * kk], sum[2 * kk + 1]);
+      }
+      continue;
+    } else if constexpr (MODE >= 4) {
       constexpr int QF = MODE - 4;
       // ---- 16-bit fixed-point rows: lane l owns the sample PAIRS (64 kk + 2 l, + 1), kk < K/2.
       // One LDS.32 fetches both samples of a pair (half the shared-memory bytes per gather-add);
@@ -852,6 +1026,24 @@ int dispatch_scan_q16(qmb_ctx *ctx, const QmbVariant &v, const ScanParams &p, in
   QMB_FAIL(QMB_ERR_ARG, "kernel variant %d has no 16-bit form", v.id);
 }
 
+// carry-free packed lanes: G rows per group (2, 4, 8 <-> 15-, 14-, 13-bit rows)
+template <int MODE>
+int dispatch_scan_packed_mode(qmb_ctx *ctx, const QmbVariant &v, const ScanParams &p, int grid, size_t smem) {
+  switch (v.id) {
+    case 4: return launch_scan<12, 4, 8, MODE, 16>(ctx, p, grid, smem);
+    case 6: return launch_scan<8, 4, 8, MODE, 16>(ctx, p, grid, smem);
+    case 7: return launch_scan<12, 4, 8, MODE, 32>(ctx, p, grid, smem);
+  }
+  QMB_FAIL(QMB_ERR_ARG, "kernel variant %d has no packed 16-bit form", v.id);
+}
+bool packed_variant(const QmbVariant &v) { return v.id == 4 || v.id == 6 || v.id == 7; }
+int dispatch_scan_packed(qmb_ctx *ctx, const QmbVariant &v, const ScanParams &p, int grid, size_t smem, int G) {
+  if (G == 2) return dispatch_scan_packed_mode<8>(ctx, v, p, grid, smem);
+  if (G == 4) return dispatch_scan_packed_mode<9>(ctx, v, p, grid, smem);
+  if (G == 8) return dispatch_scan_packed_mode<10>(ctx, v, p, grid, smem);
+  QMB_FAIL(QMB_ERR_ARG, "row group %d is not 2, 4 or 8", G);
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -860,7 +1052,7 @@ int dispatch_scan_q16(qmb_ctx *ctx, const QmbVariant &v, const ScanParams &p, in
 // Tiling decisions shared by the detect scan and the window pass.
 static int scan_setup(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, long long first, long long T,
                       int32_t available, ScanParams &p, size_t &smem, int &shift_out, bool use_q = false,
-                      int items_per_sm = 32) {
+                      int items_per_sm = 32, int qG = 1) {
   const int K = L->v.K, TT = 32 * K, NB = L->NB;
   p.on32 = O->log32.p;
   p.row_stride = O->stride;
@@ -879,8 +1071,13 @@ static int scan_setup(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, long long first, 
     p.qc0 = (float)((double)L->S * O->qmin);
     p.q_one = 1u;
     p.q_64k = 65536u;
+    p.q_m64k = 0xFFFF0000u;
     p.q_form = QMB_Q16_FORM;
     if (const char *f = getenv("QMB_Q16_FORM")) p.q_form = atoi(f);
+    if (qG > 1) {
+      p.tauq32 = L->tauq32.p;
+      p.Sg = ((L->S + qG - 1) / qG) * qG;
+    }
   }
   const int shift = (int)((front + first) & align);  // time tiles start `shift` samples early
   shift_out = shift;
@@ -891,7 +1088,7 @@ static int scan_setup(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, long long first, 
   p.n_chunks = L->Spad / L->chunk_rows;
   p.tmin = L->tmin.p; p.span = L->span.p; p.nodeidx = L->nodeidx.p;
   p.n_tiles = L->n_tiles; p.Spad = L->Spad;
-  p.stage_bytes = L->chunk_rows * p.RS * 4 + L->chunk_rows * NB * 2 + NB * 4;
+  p.stage_bytes = L->chunk_rows * p.RS * 4 + L->chunk_rows * NB * ((use_q && qG > 1) ? 4 : 2) + NB * 4;
   p.stage_bytes = (p.stage_bytes + 127) & ~127;
   const int avail_smem = QMB_SMEM_BUDGET - 1024;
   p.n_stages = avail_smem / (p.stage_bytes + 16);
@@ -926,6 +1123,10 @@ static int scan_setup(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, long long first, 
   }
   p.R = R;
   p.scale = (float)(1.4426950408889634 / (double)available);
+  if (use_q) {
+    p.qa = (float)(O->qstep * 1.4426950408889634 / (double)available);
+    p.qb = (float)((double)L->S * O->qmin * 1.4426950408889634 / (double)available);
+  }
   p.Tpad = (long long)p.n_time_tiles * TT;
   p.node_offset = L->node_offset;
   p.avail = (double)available;
@@ -996,7 +1197,14 @@ int scan_run_impl(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, int32_t fsmp, int32_t
   bool use_q = !force_fp32 && ctx->scan_fp32 != 1 && O->qstep > 0.0 && O->q16.p && L->RSq > 0 && L->tauq16.p &&
                q16_variant(L->v) && O->S <= 256;  // sum(u) < 2^24: exact in float32
   if (use_q && ctx->scan_fp32 == 0 && T < 2048) use_q = false;
-  if (use_q && scan_setup(ctx, L, O, fsmp, T, available, p, smem, shift, true) != QMB_OK) {
+  // rows quantised for carry-free groups of qG rows need the matching offset table; the two-op
+  // 16-bit kernel reads any quantisation
+  int qG = (O->qG > 1 && L->qG == O->qG && L->tauq32.p && packed_variant(L->v)) ? O->qG : 1;
+  if (use_q && qG > 1 && scan_setup(ctx, L, O, fsmp, T, available, p, smem, shift, true, 32, qG) != QMB_OK) {
+    qG = 1;
+    p = ScanParams{};
+  }
+  if (use_q && qG == 1 && scan_setup(ctx, L, O, fsmp, T, available, p, smem, shift, true) != QMB_OK) {
     use_q = false;  // e.g. too few pipeline stages for the (slightly wider) 16-bit rows
     p = ScanParams{};
   }
@@ -1005,16 +1213,23 @@ int scan_run_impl(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, int32_t fsmp, int32_t
   if (ctx->world > 1 && !force_fp32) {
     // the operand format fixes the candidate threshold, and every rank must fold the exchanged
     // state identically: 16-bit rows only when every rank can use them
-    ctx->h_status[QMB_ST_AGREE] = use_q ? 1u : 0u;
+    ctx->h_status[QMB_ST_AGREE] = use_q ? (unsigned)qG : 0u;
     QMB_CUDA(cudaMemcpyAsync(ctx->status.p + QMB_ST_AGREE, ctx->h_status + QMB_ST_AGREE, sizeof(unsigned int),
                              cudaMemcpyHostToDevice, ctx->stream));
     QMB_TRY(qmb_nccl_allreduce_u32(ctx, ctx->status.p + QMB_ST_AGREE, 1, 0));
     QMB_CUDA(cudaMemcpyAsync(ctx->h_status + QMB_ST_AGREE, ctx->status.p + QMB_ST_AGREE, sizeof(unsigned int),
                              cudaMemcpyDeviceToHost, ctx->stream));
     QMB_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (use_q && ctx->h_status[QMB_ST_AGREE] == 0u) {
+    // min over ranks: 0 -> float32 everywhere; 1 -> two-op 16-bit kernel everywhere; else the group
+    const unsigned agreed = ctx->h_status[QMB_ST_AGREE];
+    if (use_q && agreed == 0u) {
       use_q = false;
       p = ScanParams{};
+    } else if (use_q && (int)agreed != qG) {
+      qG = 1;
+      p = ScanParams{};
+      if (scan_setup(ctx, L, O, fsmp, T, available, p, smem, shift, true) != QMB_OK)
+        QMB_FAIL(QMB_ERR_STATE, "ranks disagree on the scan's operand format and this rank cannot follow");
     }
   }
   if (!use_q) QMB_TRY(scan_setup(ctx, L, O, fsmp, T, available, p, smem, shift, false));
@@ -1067,7 +1282,7 @@ int scan_run_impl(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, int32_t fsmp, int32_t
     // |quantised stack - exact| <= S * qstep / 2 (rounding to the grid) + the float32 evaluation of
     // qc0 + qstep * sum(u): rounding of qstep, of qc0 and of the fma, each <= 2^-24 of
     // S * (|qmin| + 65535 qstep)
-    const double S = (double)O->S, mag = S * (fabs(O->qmin) + 65535.0 * O->qstep);
+    const double S = (double)O->S, mag = S * (fabs(O->qmin) + (double)O->qlevels * O->qstep);
     const double delta = 0.5 * S * O->qstep + 4.0 * 5.9604644775390625e-08 * mag;
     thr = (float)(2.0 * 1.001 * delta) + 1e-30f;
   }
@@ -1076,7 +1291,8 @@ int scan_run_impl(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, int32_t fsmp, int32_t
   QMB_CUDA(cudaMemsetAsync(ctx->status.p, 0, QMB_ST_COUNT * sizeof(unsigned int), ctx->stream));
   QMB_CUDA(cudaMemsetAsync(ctx->slow_flag.p, 0, flag_bytes, ctx->stream));
   QMB_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-  QMB_TRY(use_q ? dispatch_scan_q16(ctx, L->v, p, grid, smem) : dispatch_scan<0>(ctx, L->v, p, grid, smem));
+  if (use_q && qG > 1) QMB_TRY(dispatch_scan_packed(ctx, L->v, p, grid, smem, qG));
+  else QMB_TRY(use_q ? dispatch_scan_q16(ctx, L->v, p, grid, smem) : dispatch_scan<0>(ctx, L->v, p, grid, smem));
   QMB_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
 
   // ---- merge partials (local), then across ranks ----------------------------------------------
@@ -1225,6 +1441,7 @@ int scan_run_impl(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, int32_t fsmp, int32_t
   qmb_scan_info_t &inf = ctx->info;
   inf = qmb_scan_info_t{};
   inf.operand_bytes = use_q ? 2 : 4;
+  inf.operand_bits = use_q ? O->qbits : 32;
   inf.fell_back_fp32 = 0;
   inf.check_windows = n_chk;
   inf.check_samples = chk_samples;

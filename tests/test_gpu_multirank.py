@@ -80,8 +80,12 @@ adv[:, 9] = 50.0
 got = eng.detect(lut, adv, prob.fsmp, prob.lsmp, cfg.n_rows)
 info = eng.last_scan_info
 assert info["fell_back_fp32"] == 1 and info["operand_bytes"] == 4, info
-want = O.detect_fused(adv, prob.traveltimes, prob.fsmp, prob.lsmp, cfg.n_rows, threads=2)
-assert np.array_equal(got[2], want[2])
+m4 = O.migrate(adv, prob.traveltimes, prob.fsmp, prob.lsmp, cfg.n_rows, threads=2)
+want = O.find_max_coa(m4, threads=2)
+flat = m4.reshape(-1, m4.shape[-1])
+bad = np.nonzero(got[2] != want[2])[0]   # rounding-level ties of these few-valued rows may resolve differently
+assert np.all(flat[got[2][bad], bad] >= want[0][bad] * (1 - 1e-13)), "argmax differs beyond rounding ties"
+np.testing.assert_allclose(got[0], want[0], rtol=1e-9)
 np.testing.assert_allclose(got[1], want[1], rtol=1e-5)
 lut.free()
 eng.close()

@@ -107,6 +107,20 @@ def _adversarial_rows(S, P, kind, rng):
     return rows
 
 
+def _assert_argmax_equal_up_to_rounding_ties(idx, map4d, rel=1e-13):
+    """These rows take a few thousand distinct values, so different nodes reach the SAME stack up to
+    the last bits of the float64 sum; which of them has the larger exp() then depends on the libm
+    (the reference itself is built -Ofast).  Where the indices differ, the node we report must hold
+    the reference's maximum to `rel`."""
+    flat = map4d.reshape(-1, map4d.shape[-1])
+    want = np.argmax(flat, axis=0)
+    bad = np.nonzero(idx != want)[0]
+    if len(bad):
+        ours = flat[idx[bad], bad]
+        assert np.all(ours >= flat[want[bad], bad] * (1.0 - rel)), "arg-max differs beyond rounding-level ties"
+    return len(bad)
+
+
 @pytest.mark.parametrize("kind", ["constant", "ramp", "steps"])
 @pytest.mark.parametrize("few_tau", [False, True])
 def test_correlated_quantisation_residuals_are_caught(kind, few_tau):
@@ -122,16 +136,17 @@ def test_correlated_quantisation_residuals_are_caught(kind, few_tau):
         tau = rng.integers(0, 3, size=grid + (S,), dtype=np.int32) * 20
     else:
         _, tau = syn.random_problem(5, grid, S, T, fsmp, lsmp)
-    want = O.detect_fused(onsets, tau, fsmp, lsmp, S, threads=8)
+    map4d = O.migrate(onsets, tau, fsmp, lsmp, S, threads=8)
+    want = O.find_max_coa(map4d, threads=8)
     got, info = _run_info("auto", onsets, tau, fsmp, lsmp, S)
-    assert np.array_equal(got[2], want[2])
+    _assert_argmax_equal_up_to_rounding_ties(got[2], map4d)
     np.testing.assert_allclose(got[0], want[0], rtol=1e-9)
     np.testing.assert_allclose(got[1], want[1], rtol=1e-5)
     assert info["check_windows"] >= 1
     assert info["fell_back_fp32"] == 1 and info["operand_bytes"] == 4 and info["check_max_rel_err"] > 2e-6
     # forced 16-bit rows: same indices and max_coa, and the reported check error IS the error
     got_q, info_q = _run_info("q16", onsets, tau, fsmp, lsmp, S)
-    assert np.array_equal(got_q[2], want[2])
+    _assert_argmax_equal_up_to_rounding_ties(got_q[2], map4d)
     np.testing.assert_allclose(got_q[0], want[0], rtol=1e-9)
     err = float(np.max(np.abs(got_q[1] - want[1]) / want[1]))
     assert info_q["operand_bytes"] == 2 and info_q["fell_back_fp32"] == 0
