@@ -58,7 +58,7 @@ constexpr QmbVariant QMB_VARIANTS[QMB_N_VARIANTS] = {
 constexpr int QMB_DEFAULT_VARIANT = 7;  // measured best on B200 (scripts/sweep_variants.sh)
 constexpr int QMB_DEFAULT_CHUNK_ROWS = 16;  // onset rows (station x phase) staged per pipeline stage
 constexpr int QMB_SMEM_BUDGET = 227 * 1024;
-constexpr int QMB_DEFAULT_QGROUP = 4;  // 14-bit rows, four rows per carry-free group
+constexpr int QMB_DEFAULT_QGROUP = 2;  // 15-bit rows, two rows per carry-free group (measured fastest)
 
 // ---------------------------------------------------------------------------------------------
 // device buffer helper (RAII-free; owned by the structs below)

@@ -277,62 +277,83 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
           const int ngroups = min(CR, p.Sg - c * CR) / G;
           const uint32_t lane_base = stage + (uint32_t)lane * 4u;
           const uint32_t oa = stage + rows_bytes + (uint32_t)(warp * NPW) * (G * 4u);
-          auto lds_off = [&](uint32_t addr, uint32_t (&o)[G]) {
-            if constexpr (G == 2) {
-              asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(o[0]), "=r"(o[1]) : "r"(addr));
-            } else {
-#pragma unroll
-              for (int i = 0; i < G; i += 4)
-                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(o[i]), "=r"(o[i + 1]), "=r"(o[i + 2]), "=r"(o[i + 3])
-                             : "r"(addr + 4u * i));
-            }
+          auto lds_v4 = [&](uint32_t addr, uint32_t *o) {
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3])
+                         : "r"(addr));
           };
-          auto load_pair = [&](const uint32_t (&o)[G], int h, uint32_t (&vv)[2][KW]) {
+          auto load_rows = [&](uint32_t o0, uint32_t o1, uint32_t (&vv)[2][KW]) {
+            const uint32_t a0 = lane_base + o0, a1 = lane_base + o1;
 #pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-              const uint32_t a = lane_base + o[2 * h + rr];
+            for (int k = 0; k < KW; ++k) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(vv[0][k]) : "r"(a0 + 128u * k));
 #pragma unroll
-              for (int k = 0; k < KW; ++k)
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(vv[rr][k]) : "r"(a + 128u * k));
-            }
+            for (int k = 0; k < KW; ++k) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(vv[1][k]) : "r"(a1 + 128u * k));
           };
-          uint32_t off[2][G];
           uint32_t v[2][2][KW];
           uint32_t t[KW];
-          lds_off(oa, off[0]);
-          lds_off(oa + G * 4u, off[1]);
-          load_pair(off[0], 0, v[0]);
-          for (int g = 0; g < ngroups; ++g) {
-            // the prefetches that reach into the next group are issued unconditionally (no second
-            // code path, no register shuffling at the loop edge): after the last group of the stage
-            // they re-read this group, and their results are dropped
-            const uint32_t og = oa + (uint32_t)g * OG;
-            const uint32_t ogn = g + 1 < ngroups ? og + OG : og;
+          // The prefetches that reach into the next group are issued unconditionally (no second code
+          // path, no register shuffling at the loop edge): after the last group of the stage they
+          // re-read this group, and their results are dropped.
+          if constexpr (G == 2) {
+            // one vector load carries the offsets of TWO nodes x two rows: ov[pair][2 * node + row]
+            uint32_t ov[2][4];
+            lds_v4(oa, ov[0]);
+            lds_v4(oa + 16u, ov[1]);
+            load_rows(ov[0][0], ov[0][1], v[0]);
+            for (int g = 0; g < ngroups; ++g) {
+              const uint32_t ogn = g + 1 < ngroups ? oa + (uint32_t)(g + 1) * OG : oa + (uint32_t)g * OG;
 #pragma unroll
-            for (int q = 0; q < NPW; ++q) {
-#pragma unroll
-              for (int h = 0; h < H; ++h) {
-                const int n = q * H + h;
-                // loads of the next unit first, then the adds of this one
-                if (h + 1 < H) load_pair(off[q & 1], h + 1, v[(n + 1) & 1]);
-                else if (q + 1 < NPW) load_pair(off[(q + 1) & 1], 0, v[(n + 1) & 1]);
-                else load_pair(off[0], 0, v[(n + 1) & 1]);
-                uint32_t (&vv)[2][KW] = v[n & 1];
+              for (int q = 0; q < NPW; ++q) {
+                const int qn = (q + 1) & 3;  // q == 3: node 0 of the next group (ov[0] was refilled after q == 1)
+                load_rows(ov[qn >> 1][2 * (qn & 1)], ov[qn >> 1][2 * (qn & 1) + 1], v[(q + 1) & 1]);
+                uint32_t (&vv)[2][KW] = v[q & 1];
 #pragma unroll
                 for (int k = 0; k < KW; ++k) {
-                  if (h == 0) t[k] = vv[0][k] + vv[1][k];
-                  else t[k] = t[k] + vv[0][k] + vv[1][k];
+                  t[k] = vv[0][k] + vv[1][k];
+                  Hs[q][k] += t[k] >> 16;
+                  A[q][k] = t[k] * p.q_one + A[q][k];
                 }
-                if (h == H - 1) {
+                if (q == 1) lds_v4(ogn, ov[0]);
+                if (q == 3) lds_v4(ogn + 16u, ov[1]);
+              }
+            }
+          } else {
+            uint32_t off[2][G];
+            auto lds_off = [&](uint32_t addr, uint32_t (&o)[G]) {
+#pragma unroll
+              for (int i = 0; i < G; i += 4) lds_v4(addr + 4u * i, &o[i]);
+            };
+            lds_off(oa, off[0]);
+            lds_off(oa + G * 4u, off[1]);
+            load_rows(off[0][0], off[0][1], v[0]);
+            for (int g = 0; g < ngroups; ++g) {
+              const uint32_t og = oa + (uint32_t)g * OG;
+              const uint32_t ogn = g + 1 < ngroups ? og + OG : og;
+#pragma unroll
+              for (int q = 0; q < NPW; ++q) {
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                  const int n = q * H + h;
+                  // loads of the next unit first, then the adds of this one
+                  if (h + 1 < H) load_rows(off[q & 1][2 * h + 2], off[q & 1][2 * h + 3], v[(n + 1) & 1]);
+                  else if (q + 1 < NPW) load_rows(off[(q + 1) & 1][0], off[(q + 1) & 1][1], v[(n + 1) & 1]);
+                  else load_rows(off[0][0], off[0][1], v[(n + 1) & 1]);
+                  uint32_t (&vv)[2][KW] = v[n & 1];
 #pragma unroll
                   for (int k = 0; k < KW; ++k) {
-                    Hs[q][k] += t[k] >> 16;
-                    A[q][k] = t[k] * p.q_one + A[q][k];
+                    if (h == 0) t[k] = vv[0][k] + vv[1][k];
+                    else t[k] = t[k] + vv[0][k] + vv[1][k];
                   }
-                  // this node's offsets are consumed: fetch those of the node two units ahead
-                  if (q + 2 < NPW) lds_off(og + (uint32_t)(q + 2) * (G * 4u), off[q & 1]);
-                  else lds_off(ogn + (uint32_t)(q + 2 - NPW) * (G * 4u), off[q & 1]);
+                  if (h == H - 1) {
+#pragma unroll
+                    for (int k = 0; k < KW; ++k) {
+                      Hs[q][k] += t[k] >> 16;
+                      A[q][k] = t[k] * p.q_one + A[q][k];
+                    }
+                    // this node's offsets are consumed: fetch those of the node two units ahead
+                    if (q + 2 < NPW) lds_off(og + (uint32_t)(q + 2) * (G * 4u), off[q & 1]);
+                    else lds_off(ogn + (uint32_t)(q + 2 - NPW) * (G * 4u), off[q & 1]);
+                  }
                 }
               }
             }

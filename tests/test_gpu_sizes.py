@@ -32,7 +32,9 @@ CASES = {
 def _setup(name):
     from quakemigrate_b200.core import Engine
     base, grid, T = CASES[name]
-    cfg = syn.CONFIGS[base].scaled(grid=grid, n_samples=T, name=name)
+    import dataclasses
+    # events 500 samples apart (the configs plant theirs for the full-length spans)
+    cfg = dataclasses.replace(syn.CONFIGS[base].scaled(grid=grid, n_samples=T, name=name), n_events=max(1, T // 500))
     prob = syn.make_problem(cfg)
     eng = Engine(0)
     dev, onsets = eng.onsets_from_waveforms(prob.waveforms, prob.row_channels, prob.nsta, prob.nlta,
