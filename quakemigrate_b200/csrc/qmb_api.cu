@@ -420,7 +420,7 @@ extern "C" int qmb_lut_free(qmb_lut_t L) {
   if (!L) return QMB_OK;
   cudaSetDevice(L->device);
   L->tau16.release(); L->tmin.release(); L->span.release(); L->nodeidx.release();
-  L->boxes.release(); L->slotmap.release(); L->tauq16.release(); L->tauq32.release();
+  L->boxes.release(); L->slotmap.release(); L->tauq16.release(); L->tauq32.release(); L->tauq16p.release();
   delete L;
   return QMB_OK;
 }

@@ -168,6 +168,7 @@ struct qmb_lut {
   // packed scan (groups of qG rows): BYTE offset of the pair inside the stage, row position included,
   // laid out [n_tiles][Spad / qG][NB][qG] so that one vector load fetches a node's offsets of a group
   DevBuf<uint32_t> tauq32;
+  DevBuf<uint16_t> tauq16p;  // qG == 2 and the stage's rows fit 64 KiB: the same offsets in 16 bits
   int32_t qG = 1;
 };
 

@@ -137,8 +137,8 @@ __global__ void __launch_bounds__(256) k_lut_tauq(const uint16_t *tau16, uint16_
 
 // byte offsets for the packed scan: [tile][row group][slot][G]; value = position of the row inside
 // its pipeline stage + the pair's word inside the row (the odd stream sits RSq * 2 bytes further)
-__global__ void __launch_bounds__(256) k_lut_tauq32(const uint16_t *tau16, uint32_t *tauq32, size_t n, int Spad, int NB,
-                                                    int CR, int G, int RSq) {
+__global__ void __launch_bounds__(256) k_lut_tauq32(const uint16_t *tau16, uint32_t *tauq32, uint16_t *tauq16p, size_t n,
+                                                    int Spad, int NB, int CR, int G, int RSq) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // index into tau16: (tile*Spad + s)*NB + slot
   if (i >= n) return;
   const unsigned t = tau16[i];
@@ -147,7 +147,9 @@ __global__ void __launch_bounds__(256) k_lut_tauq32(const uint16_t *tau16, uint3
   const int s = (int)(js % Spad);
   const size_t j = js / Spad;
   const uint32_t off = (uint32_t)(s % CR) * (uint32_t)RSq * 4u + 4u * (t >> 1) + (t & 1u) * (uint32_t)RSq * 2u;
-  tauq32[((j * (size_t)(Spad / G) + (size_t)(s / G)) * NB + slot) * G + (s % G)] = off;
+  const size_t o = ((j * (size_t)(Spad / G) + (size_t)(s / G)) * NB + slot) * G + (s % G);
+  tauq32[o] = off;
+  if (tauq16p) tauq16p[o] = (uint16_t)off;
 }
 
 }  // namespace
@@ -285,8 +287,12 @@ static int lut_build_variant(qmb_ctx *ctx, qmb_lut *L, const int32_t *d_raw, con
     if (ctx->scan_qgroup > 1 && (L->chunk_rows % ctx->scan_qgroup) == 0 && L->v.NPW == 4) {
       L->qG = ctx->scan_qgroup;
       QMB_TRY(L->tauq32.ensure(n));
-      k_lut_tauq32<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(L->tau16.p, L->tauq32.p, n, L->Spad, L->NB,
-                                                                        L->chunk_rows, L->qG, L->RSq);
+      // 16-bit form for groups of two rows when every offset of a stage fits
+      L->tauq16p.release();
+      const long long max_off = (long long)(L->chunk_rows - 1) * L->RSq * 4 + 4LL * (L->max_span / 2) + 2LL * L->RSq;
+      if (L->qG == 2 && max_off < 65536) QMB_TRY(L->tauq16p.ensure(n));
+      k_lut_tauq32<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(L->tau16.p, L->tauq32.p, L->tauq16p.p, n,
+                                                                        L->Spad, L->NB, L->chunk_rows, L->qG, L->RSq);
       ctx->launches++;
       QMB_CUDA(cudaGetLastError());
     }
@@ -294,6 +300,7 @@ static int lut_build_variant(qmb_ctx *ctx, qmb_lut *L, const int32_t *d_raw, con
     L->RSq = 0;
     L->tauq16.release();
     L->tauq32.release();
+    L->tauq16p.release();
     L->qG = 1;
   }
   return QMB_OK;

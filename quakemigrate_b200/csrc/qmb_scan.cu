@@ -111,6 +111,7 @@ struct ScanParams {
   // MODE 8+ (carry-free packed lanes): rows quantised to 16 - log2(G) bits, G rows are added word-wise
   // before the halves are split; tauq32 = byte offsets [tile][row group][slot][G]; Sg = S rounded up to G
   const uint32_t *tauq32;
+  const uint16_t *tauq16p;  // MODE 11: 16-bit byte offsets, [tile][row pair][slot][2]
   int Sg;
   float qa, qb;  // exp2 argument of a stack: qa * sum(u) + qb = (qc0 + qstep * sum(u)) * scale
   long long row_stride;  // elements
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
   // stage layout: [16 rows x RS floats][16 x NB uint16 tau][NB uint32 node index]
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t rows_bytes = (uint32_t)CR * p.RS * 4u;
-  constexpr uint32_t tau_bytes = (uint32_t)CR * NB * (MODE >= 8 ? 4u : 2u);
+  constexpr uint32_t tau_bytes = (uint32_t)CR * NB * ((MODE >= 8 && MODE != 11) ? 4u : 2u);
   const uint32_t bar_base = smem_base + (uint32_t)p.n_stages * p.stage_bytes;  // full[], then empty[]
 
   if (threadIdx.x == 0) {
@@ -210,7 +211,9 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
                      bytes, full);
           }
           if (lane == 0) {
-            if constexpr (MODE >= 8)
+            if constexpr (MODE == 11)
+              bulk_g2s(stage + rows_bytes, p.tauq16p + ((size_t)j * p.Spad + (size_t)c * CR) * NB, tau_bytes, full);
+            else if constexpr (MODE >= 8)
               bulk_g2s(stage + rows_bytes, p.tauq32 + ((size_t)j * p.Spad + (size_t)c * CR) * NB, tau_bytes, full);
             else
               bulk_g2s(stage + rows_bytes, p.tau16 + ((size_t)j * p.Spad + (size_t)c * CR) * NB, tau_bytes, full);
@@ -249,11 +252,13 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
       //   Hs += t >> 16 ; A += t    (once per G rows)
       // against two instructions per word for full 16-bit rows.  Offsets are byte offsets inside
       // the stage (row position included), G of them per (row group, node) in one vector load.
-      constexpr int G = 1 << (MODE - 7);
+      // MODE 11: G = 2 with 16-bit byte offsets (row position included), two per 32-bit word
+      constexpr bool HALF_OFFSETS = MODE == 11;
+      constexpr int G = HALF_OFFSETS ? 2 : 1 << (MODE - 7);
       constexpr int H = G / 2;  // row pairs per group
       static_assert(NPW == 4 && (K % 2) == 0 && (CR % G) == 0 && G >= 2 && G <= 8, "packed scan geometry");
       constexpr int KW = K / 2;
-      constexpr uint32_t OG = (uint32_t)NB * G * 4u;  // offset bytes per row group
+      constexpr uint32_t OG = (uint32_t)NB * G * (HALF_OFFSETS ? 2u : 4u);  // offset bytes per row group
       int M1[K], M2[K], M3[K];  // running top-3 of the integer stacks (sum of the quantised rows)
 #pragma unroll
       for (int k = 0; k < K; ++k) M1[k] = M2[k] = M3[k] = -1;
@@ -276,7 +281,7 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
           }
           const int ngroups = min(CR, p.Sg - c * CR) / G;
           const uint32_t lane_base = stage + (uint32_t)lane * 4u;
-          const uint32_t oa = stage + rows_bytes + (uint32_t)(warp * NPW) * (G * 4u);
+          const uint32_t oa = stage + rows_bytes + (uint32_t)(warp * NPW) * (G * (HALF_OFFSETS ? 2u : 4u));
           auto lds_v4 = [&](uint32_t addr, uint32_t *o) {
             asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                          : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3])
@@ -294,7 +299,38 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) k_scan(const ScanParams p) {
           // The prefetches that reach into the next group are issued unconditionally (no second code
           // path, no register shuffling at the loop edge): after the last group of the stage they
           // re-read this group, and their results are dropped.
-          if constexpr (G == 2) {
+          if constexpr (HALF_OFFSETS) {
+            // one 64-bit load carries the offsets of TWO nodes x two rows, 16 bits each:
+            // ow[pair][node] = offset(row 0) | offset(row 1) << 16 -- half the shared-memory wavefronts
+            // of the 32-bit form (a broadcast vector load costs one wavefront per 8 bytes)
+            uint32_t ow[2][2];
+            auto lds_v2 = [&](uint32_t addr, uint32_t *o) {
+              asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(o[0]), "=r"(o[1]) : "r"(addr));
+            };
+            auto load_node = [&](uint32_t w, uint32_t (&vv)[2][KW]) { load_rows(w & 0xffffu, w >> 16, vv); };
+            lds_v2(oa, ow[0]);
+            lds_v2(oa + 8u, ow[1]);
+            load_node(ow[0][0], v[0]);
+            auto group = [&](uint32_t ogn, auto last_tag) {
+              constexpr bool LAST = decltype(last_tag)::value;  // last group of the stage: nothing to prefetch
+#pragma unroll
+              for (int q = 0; q < NPW; ++q) {
+                const int qn = (q + 1) & 3;  // q == 3: node 0 of the next group (ow[0] was refilled after q == 1)
+                if (!(LAST && q == 3)) load_node(ow[qn >> 1][qn & 1], v[(q + 1) & 1]);
+                uint32_t (&vv)[2][KW] = v[q & 1];
+#pragma unroll
+                for (int k = 0; k < KW; ++k) {
+                  t[k] = vv[0][k] + vv[1][k];
+                  Hs[q][k] += t[k] >> 16;
+                  A[q][k] = t[k] * p.q_one + A[q][k];
+                }
+                if (!LAST && q == 1) lds_v2(ogn, ow[0]);
+                if (!LAST && q == 3) lds_v2(ogn + 8u, ow[1]);
+              }
+            };
+            for (int g = 0; g + 1 < ngroups; ++g) group(oa + (uint32_t)(g + 1) * OG, std::false_type{});
+            group(0u, std::true_type{});
+          } else if constexpr (G == 2) {
             // one vector load carries the offsets of TWO nodes x two rows: ov[pair][2 * node + row]
             uint32_t ov[2][4];
             lds_v4(oa, ov[0]);
@@ -1059,6 +1095,7 @@ int dispatch_scan_packed_mode(qmb_ctx *ctx, const QmbVariant &v, const ScanParam
 }
 bool packed_variant(const QmbVariant &v) { return v.id == 4 || v.id == 6 || v.id == 7; }
 int dispatch_scan_packed(qmb_ctx *ctx, const QmbVariant &v, const ScanParams &p, int grid, size_t smem, int G) {
+  if (G == 2 && p.tauq16p && !getenv("QMB_WIDE_OFFSETS")) return dispatch_scan_packed_mode<11>(ctx, v, p, grid, smem);
   if (G == 2) return dispatch_scan_packed_mode<8>(ctx, v, p, grid, smem);
   if (G == 4) return dispatch_scan_packed_mode<9>(ctx, v, p, grid, smem);
   if (G == 8) return dispatch_scan_packed_mode<10>(ctx, v, p, grid, smem);
@@ -1097,6 +1134,7 @@ static int scan_setup(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, long long first, 
     if (const char *f = getenv("QMB_Q16_FORM")) p.q_form = atoi(f);
     if (qG > 1) {
       p.tauq32 = L->tauq32.p;
+      p.tauq16p = L->tauq16p.p;
       p.Sg = ((L->S + qG - 1) / qG) * qG;
     }
   }
@@ -1109,7 +1147,8 @@ static int scan_setup(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, long long first, 
   p.n_chunks = L->Spad / L->chunk_rows;
   p.tmin = L->tmin.p; p.span = L->span.p; p.nodeidx = L->nodeidx.p;
   p.n_tiles = L->n_tiles; p.Spad = L->Spad;
-  p.stage_bytes = L->chunk_rows * p.RS * 4 + L->chunk_rows * NB * ((use_q && qG > 1) ? 4 : 2) + NB * 4;
+  const bool half_offsets = use_q && qG == 2 && L->tauq16p.p != nullptr;
+  p.stage_bytes = L->chunk_rows * p.RS * 4 + L->chunk_rows * NB * ((use_q && qG > 1 && !half_offsets) ? 4 : 2) + NB * 4;
   p.stage_bytes = (p.stage_bytes + 127) & ~127;
   const int avail_smem = QMB_SMEM_BUDGET - 1024;
   p.n_stages = avail_smem / (p.stage_bytes + 16);
