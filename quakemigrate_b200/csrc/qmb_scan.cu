@@ -1095,7 +1095,7 @@ int dispatch_scan_packed_mode(qmb_ctx *ctx, const QmbVariant &v, const ScanParam
 }
 bool packed_variant(const QmbVariant &v) { return v.id == 4 || v.id == 6 || v.id == 7; }
 int dispatch_scan_packed(qmb_ctx *ctx, const QmbVariant &v, const ScanParams &p, int grid, size_t smem, int G) {
-  if (G == 2 && p.tauq16p && !getenv("QMB_WIDE_OFFSETS")) return dispatch_scan_packed_mode<11>(ctx, v, p, grid, smem);
+  if (G == 2 && p.tauq16p) return dispatch_scan_packed_mode<11>(ctx, v, p, grid, smem);
   if (G == 2) return dispatch_scan_packed_mode<8>(ctx, v, p, grid, smem);
   if (G == 4) return dispatch_scan_packed_mode<9>(ctx, v, p, grid, smem);
   if (G == 8) return dispatch_scan_packed_mode<10>(ctx, v, p, grid, smem);
@@ -1134,7 +1134,7 @@ static int scan_setup(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, long long first, 
     if (const char *f = getenv("QMB_Q16_FORM")) p.q_form = atoi(f);
     if (qG > 1) {
       p.tauq32 = L->tauq32.p;
-      p.tauq16p = L->tauq16p.p;
+      p.tauq16p = getenv("QMB_WIDE_OFFSETS") ? nullptr : L->tauq16p.p;  // tuning: force the 32-bit offsets
       p.Sg = ((L->S + qG - 1) / qG) * qG;
     }
   }
@@ -1147,7 +1147,7 @@ static int scan_setup(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, long long first, 
   p.n_chunks = L->Spad / L->chunk_rows;
   p.tmin = L->tmin.p; p.span = L->span.p; p.nodeidx = L->nodeidx.p;
   p.n_tiles = L->n_tiles; p.Spad = L->Spad;
-  const bool half_offsets = use_q && qG == 2 && L->tauq16p.p != nullptr;
+  const bool half_offsets = use_q && qG == 2 && L->tauq16p.p != nullptr && !getenv("QMB_WIDE_OFFSETS");
   p.stage_bytes = L->chunk_rows * p.RS * 4 + L->chunk_rows * NB * ((use_q && qG > 1 && !half_offsets) ? 4 : 2) + NB * 4;
   p.stage_bytes = (p.stage_bytes + 127) & ~127;
   const int avail_smem = QMB_SMEM_BUDGET - 1024;

@@ -32,19 +32,19 @@ class Grid3D:
         self.unit_conversion_factor = 1.0
 
     def index2grid(self, value, inverse=False, unravel=False):
-        """lut.py:142-180."""
+        """
+        Grid index <-> grid coordinate (contract of lut.py:142-180): ``value`` is one ``[i, j, k]``,
+        an ``(n, 3)`` array of them, or -- with ``unravel`` -- flat C-order node indices (x slowest,
+        z fastest, lut.py:165-166).  Always returns an ``(n, 3)`` array; the forward map multiplies,
+        then adds (the order the golden X/Y/Z integers of the reference's .scanmseed depend on).
+        """
+        idx = np.asarray(value)
         if unravel:
-            value = np.column_stack(np.unravel_index(value, self.node_count))
-        else:
-            value = np.array(value)
+            idx = np.stack(np.unravel_index(idx.reshape(-1), tuple(int(n) for n in self.node_count)), axis=-1)
+        idx = np.atleast_2d(idx)
         if inverse:
-            out = np.rint((value - self.ll_corner) / self.node_spacing)
-            out = np.vstack(out.astype(int))
-        else:
-            out = np.vstack(self.ll_corner + (value * self.node_spacing))
-        if out.shape[1] == 1:
-            out = out.T
-        return out
+            return np.rint((idx - self.ll_corner) / self.node_spacing).astype(int)
+        return self.ll_corner + idx * self.node_spacing
 
     def index2coord(self, value, inverse=False, unravel=False):
         """lut.py:211-243 with the projection step delegated to ``grid2coord``."""
@@ -67,33 +67,34 @@ class LUT(Grid3D):
     def __getitem__(self, key):
         return self.traveltimes[key]
 
+    def _grid(self, station, phase):
+        """One travel-time grid; NonLinLoc imports store it under ``TIME_<phase>`` (lut.py:531-534)."""
+        grids = self.traveltimes[station]
+        return grids[phase] if phase in grids else grids[f"TIME_{phase}"]  # KeyError: phase missing
+
+    def _stack(self, pairs):
+        pairs = list(pairs)
+        out = np.empty(tuple(int(n) for n in self.node_count) + (len(pairs),), dtype=np.double)
+        for row, (station, phase) in enumerate(pairs):
+            out[..., row] = self._grid(station, phase)
+        return out
+
     def serve_traveltimes(self, sampling_rate, availability=None):
-        """lut.py:502-538 (same ordering, same ``TIME_<phase>`` fallback, same rounding)."""
+        """
+        Contract of lut.py:502-538: the int32 sample-offset stack ``(nx, ny, nz, n_rows)``, one row
+        per AVAILABLE ``"<station>_<phase>"`` key in the order of the availability dict (every
+        station/phase, phase-outer, without one), ``rint(seconds * sampling_rate)``.
+        """
         if availability is None:
-            traveltimes = self._serve_traveltimes(self.phases)
+            pairs = [(station, phase) for phase in self.phases for station in self.stations]
         else:
-            traveltimes = []
-            for key, available in availability.items():
-                station, phase = key.split("_")
-                if available == 1:
-                    try:
-                        traveltimes.append(self[station][phase])
-                    except KeyError:
-                        traveltimes.append(self[station][f"TIME_{phase}"])
-            traveltimes = np.stack(traveltimes, axis=-1)
-        return np.rint(traveltimes * sampling_rate).astype(np.int32)
+            pairs = [tuple(key.rsplit("_", 1)) for key, available in availability.items() if available == 1]
+        return np.rint(self._stack(pairs) * sampling_rate).astype(np.int32)
 
     def _serve_traveltimes(self, phases, stations=None):
-        """lut.py:576-603: phase-outer, station-inner."""
+        """Float64 stack for the given phases, phase-outer / station-inner (contract of lut.py:576-603)."""
         stations = self.stations if stations is None else stations
-        traveltimes = []
-        for phase in phases:
-            for station in stations:
-                try:
-                    traveltimes.append(self[station][phase])
-                except KeyError:
-                    traveltimes.append(self[station][f"TIME_{phase}"])
-        return np.stack(traveltimes, axis=-1)
+        return self._stack((station, phase) for phase in phases for station in stations)
 
     def decimate(self, df, inplace=False):
         """
