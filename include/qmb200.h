@@ -21,7 +21,7 @@
  *      like the reference (C never allocates, frees or retains host pointers).
  *
  * There is NO CPU fallback anywhere behind this header: without a CUDA device every T2 call
- * returns QMB_ERR_CUDA and every T1 call aborts with a message on stderr.
+ * returns QMB_ERR_CUDA and every T1 call fails (see qmb_legacy_status).
  */
 #ifndef QMB200_H
 #define QMB200_H
@@ -56,6 +56,15 @@ void find_max_coa(double *map4d, double *max_coa, double *max_norm_coa, int64_t 
 void overlapping_sta_lta(const double *signal, const stalta_header *head, double *onset);
 void centred_sta_lta(const double *signal, const stalta_header *head, double *onset);
 void recursive_sta_lta(const double *signal, const stalta_header *head, double *onset);
+
+/* The five symbols above return void like the reference's, so a failure (no device, out of memory,
+ * a travel time beyond the post-pad -- where the reference would read past its onset rows) cannot
+ * be returned: it is recorded per thread, reported on stderr, and the call returns with the output
+ * buffers untouched.  qmb_legacy_status() returns the status of this thread's last T1 call (QMB_OK
+ * = 0, else a QMB_ERR_* code; message in qmb_last_error()) and clears it; quakemigrate_b200.core
+ * checks it after every call and raises.  Set QMB_LEGACY_ABORT=1 to abort() instead -- the only way
+ * an unmodified quakemigrate.core, which never asks, can be stopped from using a zero map. */
+int qmb_legacy_status(void);
 
 /* ------------------------------------------------------------------------------------------
  * T2 -- fused device-resident path

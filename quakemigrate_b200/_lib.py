@@ -74,6 +74,7 @@ SIGNATURES = {
     "overlapping_sta_lta": (None, [c_dPt, stalta_header_pt, c_dPt]),
     "centred_sta_lta": (None, [c_dPt, stalta_header_pt, c_dPt]),
     "recursive_sta_lta": (None, [c_dPt, stalta_header_pt, c_dPt]),
+    "qmb_legacy_status": (ctypes.c_int, []),
     # T2
     "qmb_last_error": (ctypes.c_char_p, []),
     "qmb_version": (ctypes.c_char_p, []),
@@ -184,6 +185,11 @@ def load() -> ctypes.CDLL:
 def check(status: int) -> None:
     if status != 0:
         raise QmbError(status, load().qmb_last_error().decode(errors="replace"))
+
+
+def check_legacy() -> None:
+    """Raise if the last reference-compatible (void) symbol called from this thread failed."""
+    check(load().qmb_legacy_status())
 
 
 def device_count() -> int:

@@ -5,8 +5,11 @@ Drop-in for :mod:`quakemigrate.core` backed by ``libqmb200.so`` (B200, sm_100a).
 Tier 1 -- same five functions, same signatures, same exceptions as the reference bindings
 (``quakemigrate/core/lib.py``): :func:`migrate`, :func:`find_max_coa`,
 :func:`overlapping_sta_lta`, :func:`centred_sta_lta`, :func:`recursive_sta_lta`.  They call the
-reference-compatible C symbols, which run on the GPU but return the full float64 volume through
-host memory, exactly like the reference.
+reference-compatible C symbols, which run on the GPU and return the full float64 volume through
+host memory like the reference does.  ``migrate`` stacks float32 log-onsets in float32 and applies
+a float64 ``exp``: its values agree with the reference to ~1e-6 relative (tests: 1e-5), not to the
+last bit; ``find_max_coa`` on a given volume is bit-identical (same node order, same compares).
+A failure inside the (void) C symbols raises :class:`QmbError` here.
 
 Tier 2 -- :class:`Engine`: device-resident travel-time tables and onsets, fused
 detect (no 4-D volume), marginal window for locate, node-sharded multi-GPU.
@@ -59,12 +62,20 @@ def migrate(onsets, traveltimes, first_idx, last_idx, available, threads):
         )
     if onsets.size < n_samples + first_idx:
         raise ValueError("Data array smaller than coalescence array.")
+    # The reference has no upper bound check on the travel times (migratelib.c:55-57): an offset
+    # beyond the post-pad reads past the onset row.  Here that is an error, raised before any work.
+    if traveltimes.size and int(np.max(traveltimes)) > last_idx:
+        raise ValueError(
+            f"Maximum travel time ({int(np.max(traveltimes))} samples) exceeds last_idx ({last_idx}): "
+            "the post-pad must cover the largest travel time (scan.py:213)."
+        )
 
     lib.migrate(
         onsets, np.ascontiguousarray(traveltimes, dtype=np.int32), map4d,
         c_int32(first_idx), c_int32(last_idx), c_int32(n_samples), c_int32(n_onsets),
         c_int32(int(available)), c_int64(n_nodes), c_int64(int(threads)),
     )
+    _lib.check_legacy()  # the C symbol is void like the reference's: failures surface here
     return map4d
 
 
@@ -80,16 +91,21 @@ def find_max_coa(map4d, threads):
         np.ascontiguousarray(map4d, dtype=np.double), max_coa, max_norm_coa, max_coa_idx,
         c_int32(n_samples), c_int64(n_nodes), c_int64(int(threads)),
     )
+    _lib.check_legacy()
     return max_coa, max_norm_coa, max_coa_idx
 
 
 def _legacy_stalta(name, prefill, signal, nsta, nlta):
     lib = _lib.load()
+    if name != "recursive_sta_lta" and nsta > nlta:
+        # onsetlib.c:44-58 subtracts samples it never added when the short window is the longer one
+        raise ValueError(f"nsta ({nsta}) must not exceed nlta ({nlta})")
     head = np.empty(1, dtype=stalta_header_t)
     head[:] = (len(signal), nsta, nlta)
     signal = np.ascontiguousarray(signal, dtype=np.double)
     onset = np.full(len(signal), prefill, dtype=np.double)
     getattr(lib, name)(signal, head, onset)
+    _lib.check_legacy()
     return onset
 
 

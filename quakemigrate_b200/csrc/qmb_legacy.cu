@@ -6,8 +6,10 @@
 // accumulated into, STA/LTA outputs arrive pre-filled), which forces the full (n_nodes, n_samples)
 // float64 volume over PCIe: they are the plumbing tier.  The fast path is the T2 API.
 #include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
+#include <vector>
 
 #include "qmb_internal.cuh"
 
@@ -16,10 +18,33 @@ namespace {
 std::mutex g_default_mu;
 qmb_ctx *g_default = nullptr;
 
-[[noreturn]] void die(const char *what) {
-  fprintf(stderr, "libqmb200: %s: %s\n(no CPU fallback exists in this library)\n", what, qmb_last_error());
-  abort();
+// The five reference symbols return void (qmlib.h:28-44), so a failure cannot be returned.  It is
+// recorded (qmb_legacy_status / qmb_last_error -- quakemigrate_b200.core checks them after every call
+// and raises), reported on stderr, and the call returns with the caller's output buffers untouched.
+// QMB_LEGACY_ABORT=1 restores a hard abort() for an unmodified quakemigrate.core, which has no way
+// of noticing the status and would otherwise go on with a zero map.
+thread_local int g_legacy_status = QMB_OK;
+
+void legacy_fail(const char *what, int status) {
+  g_legacy_status = status ? status : QMB_ERR_CUDA;
+  fprintf(stderr, "libqmb200: %s failed: %s\n(no CPU fallback exists in this library; output left untouched)\n", what,
+          qmb_last_error());
+  const char *ab = getenv("QMB_LEGACY_ABORT");
+  if (ab && atoi(ab) != 0) abort();
 }
+
+struct DevMem {  // device allocation released on scope exit
+  void *p = nullptr;
+  ~DevMem() {
+    if (p) cudaFree(p);
+  }
+  int alloc(size_t bytes) {
+    QMB_CUDA(cudaMalloc(&p, bytes));
+    return QMB_OK;
+  }
+  template <typename T>
+  T *as() const { return (T *)p; }
+};
 
 // per-sample (max, first arg-max, sum) over a slab of nodes; one thread per sample, nodes split
 // across blockIdx.y groups.  Node order inside a group is ascending, ">" is strict, so ties keep
@@ -75,11 +100,130 @@ qmb_ctx *qmb_default_ctx() {
   if (!g_default) {
     const char *d = getenv("QMB_DEVICE");
     qmb_ctx_t c = nullptr;
-    if (qmb_ctx_create(d ? atoi(d) : 0, &c) != QMB_OK) die("cannot create the default CUDA context");
+    if (qmb_ctx_create(d ? atoi(d) : 0, &c) != QMB_OK) return nullptr;  // message in qmb_last_error
     g_default = c;
   }
   return g_default;
 }
+
+extern "C" int qmb_legacy_status(void) {
+  const int s = g_legacy_status;
+  g_legacy_status = QMB_OK;
+  return s;
+}
+
+namespace {
+
+int migrate_impl(double *onsets, int32_t *lookup_tables, double *map4d, int32_t fsmp, int32_t lsmp,
+                 int32_t n_samples, int32_t n_stations, int32_t available, int64_t n_nodes) {
+  qmb_ctx *ctx = qmb_default_ctx();
+  if (!ctx) return QMB_ERR_CUDA;
+  QMB_CUDA(cudaSetDevice(ctx->device));
+  const int64_t P = (int64_t)fsmp + lsmp + n_samples;
+
+  // onsets: upload once, skip the clip/log
+  struct OnsetsGuard {
+    qmb_onsets *O = new qmb_onsets();
+    ~OnsetsGuard() { qmb_onsets_free(O); }
+  } og;
+  qmb_onsets *O = og.O;
+  O->ctx = ctx; O->device = ctx->device; O->S = n_stations; O->P = P;
+  {
+    DevMem lin;
+    const size_t on_bytes = (size_t)n_stations * P * sizeof(double);
+    QMB_TRY(lin.alloc(on_bytes));
+    QMB_CUDA(cudaMemcpyAsync(lin.p, onsets, on_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    QMB_TRY(qmb_onsets_prepare(ctx, O, lin.as<double>(), 1));
+    QMB_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+
+  // node slabs sized so that the float64 slab of the volume stays under ~2 GiB on the device
+  int64_t slab = (int64_t)((2ull << 30) / ((size_t)n_samples * sizeof(double)));
+  slab = (slab / 64) * 64;
+  if (slab < 64) slab = 64;
+  DevMem map;
+  const int64_t slab_alloc = slab < n_nodes ? slab : n_nodes;
+  QMB_TRY(map.alloc((size_t)slab_alloc * n_samples * sizeof(double)));
+
+  for (int64_t n0 = 0; n0 < n_nodes; n0 += slab) {
+    const int64_t nn = (n_nodes - n0 < slab) ? n_nodes - n0 : slab;
+    // pseudo-grid (ceil(nn/16), 4, 4): 64 consecutive flat nodes form one tile
+    struct LutGuard {
+      qmb_lut *L = new qmb_lut();
+      ~LutGuard() { qmb_lut_free(L); }
+    } lg;
+    qmb_lut *L = lg.L;
+    L->ctx = ctx;
+    L->device = ctx->device;
+    L->nxl = (int32_t)((nn + 15) / 16); L->ny = 4; L->nz = 4; L->S = n_stations;
+    L->node_offset = 0; L->n_global = nn; L->n_local = nn;
+    {
+      DevMem raw;
+      const size_t raw_bytes = (size_t)nn * n_stations * sizeof(int32_t);
+      QMB_TRY(raw.alloc(raw_bytes));
+      QMB_CUDA(cudaMemcpyAsync(raw.p, lookup_tables + (size_t)n0 * n_stations, raw_bytes, cudaMemcpyHostToDevice,
+                               ctx->stream));
+      QMB_TRY(qmb_lut_build(ctx, L, raw.as<int32_t>()));
+    }
+    if (L->max_tau > lsmp)
+      QMB_FAIL(QMB_ERR_ARG,
+               "travel time %d samples > lsmp %d: the reference reads past the onset rows here (post_pad must be "
+               ">= the maximum travel time, scan.py:213)",
+               L->max_tau, lsmp);
+    const size_t map_bytes = (size_t)nn * n_samples * sizeof(double);
+    // the reference accumulates into the caller's (zeroed) array: bring its contents in
+    QMB_CUDA(cudaMemcpyAsync(map.p, map4d + (size_t)n0 * n_samples, map_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    QMB_TRY(qmb_window_run(ctx, L, O, fsmp, lsmp, available, 0, n_samples, nullptr, map.as<double>(), 1));
+    QMB_CUDA(cudaMemcpyAsync(map4d + (size_t)n0 * n_samples, map.p, map_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    QMB_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return QMB_OK;
+}
+
+int find_max_coa_impl(double *map4d, double *max_coa, double *max_norm_coa, int64_t *max_coa_idx, int32_t n_samples,
+                      int64_t n_nodes) {
+  qmb_ctx *ctx = qmb_default_ctx();
+  if (!ctx) return QMB_ERR_CUDA;
+  QMB_CUDA(cudaSetDevice(ctx->device));
+  int64_t slab = (int64_t)((2ull << 30) / ((size_t)n_samples * sizeof(double)));
+  if (slab < 1) slab = 1;
+  if (slab > n_nodes) slab = n_nodes;
+  const int groups = 64;
+  const size_t T = (size_t)n_samples;
+  DevMem map, gmax, gsum, gidx, rmax, rsum, ridx, norm;
+  QMB_TRY(map.alloc((size_t)slab * T * 8));
+  QMB_TRY(gmax.alloc(groups * T * 8)); QMB_TRY(gsum.alloc(groups * T * 8)); QMB_TRY(gidx.alloc(groups * T * 8));
+  QMB_TRY(rmax.alloc(T * 8)); QMB_TRY(rsum.alloc(T * 8)); QMB_TRY(ridx.alloc(T * 8)); QMB_TRY(norm.alloc(T * 8));
+  const int tb = (n_samples + 127) / 128;
+  int first = 1;
+  for (int64_t n0 = 0; n0 < n_nodes; n0 += slab) {
+    const int64_t nn = (n_nodes - n0 < slab) ? n_nodes - n0 : slab;
+    QMB_CUDA(cudaMemcpyAsync(map.p, map4d + (size_t)n0 * T, (size_t)nn * T * 8, cudaMemcpyHostToDevice, ctx->stream));
+    k_colreduce<<<dim3(tb, groups), 128, 0, ctx->stream>>>(map.as<double>(), nn, n_samples, n0, groups, gmax.as<double>(),
+                                                           gidx.as<long long>(), gsum.as<double>());
+    k_colfold<<<tb, 128, 0, ctx->stream>>>(gmax.as<double>(), gidx.as<long long>(), gsum.as<double>(), groups, n_samples,
+                                           rmax.as<double>(), ridx.as<long long>(), rsum.as<double>(), first);
+    ctx->launches += 2;
+    QMB_CUDA(cudaGetLastError());
+    first = 0;
+  }
+  k_colfinish<<<tb, 128, 0, ctx->stream>>>(rmax.as<double>(), rsum.as<double>(), (double)n_nodes, n_samples, norm.as<double>());
+  ctx->launches++;
+  QMB_CUDA(cudaGetLastError());
+  // results land in scratch first: the caller's arrays are written only when everything worked
+  std::vector<double> h_max(T), h_norm(T);
+  std::vector<int64_t> h_idx(T);
+  QMB_CUDA(cudaMemcpyAsync(h_max.data(), rmax.p, T * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  QMB_CUDA(cudaMemcpyAsync(h_norm.data(), norm.p, T * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  QMB_CUDA(cudaMemcpyAsync(h_idx.data(), ridx.p, T * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  QMB_CUDA(cudaStreamSynchronize(ctx->stream));
+  memcpy(max_coa, h_max.data(), T * 8);
+  memcpy(max_norm_coa, h_norm.data(), T * 8);
+  memcpy(max_coa_idx, h_idx.data(), T * 8);
+  return QMB_OK;
+}
+
+}  // namespace
 
 // migrate(), quakemigrate/core/src/migratelib.c:40-65.  `onsets` are LOG onsets here (the Python
 // wrapper clips and logs before the call, lib.py:93-94).  `threads` is accepted and ignored.
@@ -87,118 +231,29 @@ extern "C" void migrate(double *onsets, int32_t *lookup_tables, double *map4d, i
                         int32_t n_samples, int32_t n_stations, int32_t available, int64_t n_nodes,
                         int64_t threads) {
   (void)threads;
+  g_legacy_status = QMB_OK;
   if (n_nodes <= 0 || n_samples <= 0 || n_stations <= 0) return;
-  qmb_ctx *ctx = qmb_default_ctx();
-  if (cudaSetDevice(ctx->device) != cudaSuccess) die("cudaSetDevice");
-  const int64_t P = (int64_t)fsmp + lsmp + n_samples;
-
-  // onsets: upload once, skip the clip/log
-  qmb_onsets *O = new qmb_onsets();
-  O->ctx = ctx; O->device = ctx->device; O->S = n_stations; O->P = P;
-  double *d_lin = nullptr;
-  const size_t on_bytes = (size_t)n_stations * P * sizeof(double);
-  if (cudaMalloc((void **)&d_lin, on_bytes) != cudaSuccess) die("cudaMalloc(onsets)");
-  if (cudaMemcpyAsync(d_lin, onsets, on_bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) die("H2D onsets");
-  if (qmb_onsets_prepare(ctx, O, d_lin, 1) != QMB_OK) die("onset preparation");
-  cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_lin);
-
-  // node slabs sized so that the float64 slab of the volume stays under ~2 GiB on the device
-  int64_t slab = (int64_t)((2ull << 30) / ((size_t)n_samples * sizeof(double)));
-  slab = (slab / 64) * 64;
-  if (slab < 64) slab = 64;
-  double *d_map = nullptr;
-  const int64_t slab_alloc = slab < n_nodes ? slab : n_nodes;
-  if (cudaMalloc((void **)&d_map, (size_t)slab_alloc * n_samples * sizeof(double)) != cudaSuccess) die("cudaMalloc(map slab)");
-
-  for (int64_t n0 = 0; n0 < n_nodes; n0 += slab) {
-    const int64_t nn = (n_nodes - n0 < slab) ? n_nodes - n0 : slab;
-    // pseudo-grid (ceil(nn/16), 4, 4): 64 consecutive flat nodes form one tile
-    qmb_lut *L = new qmb_lut();
-    L->ctx = ctx;
-    L->device = ctx->device;
-    L->nxl = (int32_t)((nn + 15) / 16); L->ny = 4; L->nz = 4; L->S = n_stations;
-    L->node_offset = 0; L->n_global = nn; L->n_local = nn;
-    int32_t *d_raw = nullptr;
-    const size_t raw_bytes = (size_t)nn * n_stations * sizeof(int32_t);
-    if (cudaMalloc((void **)&d_raw, raw_bytes) != cudaSuccess) die("cudaMalloc(lut slab)");
-    if (cudaMemcpyAsync(d_raw, lookup_tables + (size_t)n0 * n_stations, raw_bytes, cudaMemcpyHostToDevice,
-                        ctx->stream) != cudaSuccess)
-      die("H2D lut");
-    if (qmb_lut_build(ctx, L, d_raw) != QMB_OK) die("travel-time table tiling");
-    cudaFree(d_raw);
-    if (L->max_tau > lsmp) {
-      qmb_set_error("travel time %d samples > lsmp %d: the reference reads out of bounds here", L->max_tau, lsmp);
-      die("migrate");
-    }
-    const size_t map_bytes = (size_t)nn * n_samples * sizeof(double);
-    // the reference accumulates into the caller's (zeroed) array: bring its contents in
-    if (cudaMemcpyAsync(d_map, map4d + (size_t)n0 * n_samples, map_bytes, cudaMemcpyHostToDevice, ctx->stream) !=
-        cudaSuccess)
-      die("H2D map4d");
-    if (qmb_window_run(ctx, L, O, fsmp, lsmp, available, 0, n_samples, nullptr, d_map, 1) != QMB_OK) die("migrate kernel");
-    if (cudaMemcpyAsync(map4d + (size_t)n0 * n_samples, d_map, map_bytes, cudaMemcpyDeviceToHost, ctx->stream) !=
-        cudaSuccess)
-      die("D2H map4d");
-    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
-      qmb_set_error("%s", cudaGetErrorString(cudaGetLastError()));
-      die("migrate");
-    }
-    qmb_lut_free(L);
-  }
-  cudaFree(d_map);
-  qmb_onsets_free(O);
+  const int rc = migrate_impl(onsets, lookup_tables, map4d, fsmp, lsmp, n_samples, n_stations, available, n_nodes);
+  if (rc != QMB_OK) legacy_fail("migrate", rc);
 }
 
 // find_max_coa(), quakemigrate/core/src/migratelib.c:85-111
 extern "C" void find_max_coa(double *map4d, double *max_coa, double *max_norm_coa, int64_t *max_coa_idx,
                              int32_t n_samples, int64_t n_nodes, int64_t threads) {
   (void)threads;
+  g_legacy_status = QMB_OK;
   if (n_nodes <= 0 || n_samples <= 0) return;
-  qmb_ctx *ctx = qmb_default_ctx();
-  if (cudaSetDevice(ctx->device) != cudaSuccess) die("cudaSetDevice");
-  int64_t slab = (int64_t)((2ull << 30) / ((size_t)n_samples * sizeof(double)));
-  if (slab < 1) slab = 1;
-  if (slab > n_nodes) slab = n_nodes;
-  const int groups = 64;
-  double *d_map, *d_gmax, *d_gsum, *d_rmax, *d_rsum, *d_norm;
-  long long *d_gidx, *d_ridx;
-  const size_t T = (size_t)n_samples;
-  if (cudaMalloc((void **)&d_map, (size_t)slab * T * 8) != cudaSuccess) die("cudaMalloc(map slab)");
-  if (cudaMalloc((void **)&d_gmax, groups * T * 8) != cudaSuccess || cudaMalloc((void **)&d_gsum, groups * T * 8) != cudaSuccess ||
-      cudaMalloc((void **)&d_gidx, groups * T * 8) != cudaSuccess || cudaMalloc((void **)&d_rmax, T * 8) != cudaSuccess ||
-      cudaMalloc((void **)&d_rsum, T * 8) != cudaSuccess || cudaMalloc((void **)&d_ridx, T * 8) != cudaSuccess ||
-      cudaMalloc((void **)&d_norm, T * 8) != cudaSuccess)
-    die("cudaMalloc(find_max_coa scratch)");
-  const int tb = (n_samples + 127) / 128;
-  int first = 1;
-  for (int64_t n0 = 0; n0 < n_nodes; n0 += slab) {
-    const int64_t nn = (n_nodes - n0 < slab) ? n_nodes - n0 : slab;
-    if (cudaMemcpyAsync(d_map, map4d + (size_t)n0 * T, (size_t)nn * T * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
-      die("H2D map4d");
-    k_colreduce<<<dim3(tb, groups), 128, 0, ctx->stream>>>(d_map, nn, n_samples, n0, groups, d_gmax, d_gidx, d_gsum);
-    k_colfold<<<tb, 128, 0, ctx->stream>>>(d_gmax, d_gidx, d_gsum, groups, n_samples, d_rmax, d_ridx, d_rsum, first);
-    ctx->launches += 2;
-    first = 0;
-  }
-  k_colfinish<<<tb, 128, 0, ctx->stream>>>(d_rmax, d_rsum, (double)n_nodes, n_samples, d_norm);
-  ctx->launches++;
-  cudaMemcpyAsync(max_coa, d_rmax, T * 8, cudaMemcpyDeviceToHost, ctx->stream);
-  cudaMemcpyAsync(max_norm_coa, d_norm, T * 8, cudaMemcpyDeviceToHost, ctx->stream);
-  cudaMemcpyAsync(max_coa_idx, d_ridx, T * 8, cudaMemcpyDeviceToHost, ctx->stream);
-  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
-    qmb_set_error("%s", cudaGetErrorString(cudaGetLastError()));
-    die("find_max_coa");
-  }
-  cudaFree(d_map); cudaFree(d_gmax); cudaFree(d_gsum); cudaFree(d_gidx); cudaFree(d_rmax); cudaFree(d_rsum);
-  cudaFree(d_ridx); cudaFree(d_norm);
+  const int rc = find_max_coa_impl(map4d, max_coa, max_norm_coa, max_coa_idx, n_samples, n_nodes);
+  if (rc != QMB_OK) legacy_fail("find_max_coa", rc);
 }
 
 static void legacy_stalta(const double *signal, const stalta_header *head, double *onset, int position,
                           const char *name) {
+  g_legacy_status = QMB_OK;
   if (!head || head->n <= 0) return;
   qmb_ctx *ctx = qmb_default_ctx();
-  if (qmb_sta_lta(ctx, signal, 1, head->n, head->nsta, head->nlta, position, onset) != QMB_OK) die(name);
+  const int rc = ctx ? qmb_sta_lta(ctx, signal, 1, head->n, head->nsta, head->nlta, position, onset) : QMB_ERR_CUDA;
+  if (rc != QMB_OK) legacy_fail(name, rc);
 }
 
 // quakemigrate/core/src/onsetlib.c:35-59
