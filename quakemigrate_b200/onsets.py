@@ -16,8 +16,14 @@ against ``quakemigrate.signal.onsets`` keeps working:
   without it, waveforms are taken as already pre-processed.
 
 Waveform containers are duck-typed: anything with ``stations``, ``starttime``, ``endtime`` and
-``channels`` (dict ``station -> {component letter -> 1-D float array}``) works;
-:class:`WaveformData` is the minimal one.
+``channels`` (dict ``station -> {component letter -> trace}``) works; :class:`WaveformData` is the
+minimal one.  A trace is a 1-D float array covering the whole timespan, or -- for gappy / short
+data -- a list of :class:`Segment` (sample offset from ``starttime``, data).  Availability follows
+``WaveformData.check_availability`` (io/data.py:509-646): flat-lined, overlapping, gappy (unless
+``allow_gaps``) or short (if ``full_timespan``) channels are dropped; with ``allow_gaps`` or
+``full_timespan=False`` the surviving segments are pre-processed one by one, tapered again, merged
+and padded with tiny values exactly like stalta.py:436-462.
+:mod:`quakemigrate_b200.reference_adapter` converts the reference's obspy-backed container.
 """
 
 from __future__ import annotations
@@ -26,7 +32,7 @@ from abc import ABC, abstractmethod
 
 import numpy as np
 
-from .synthetic import time2sample, trim2sample
+from .util import time2sample, trim2sample
 
 
 class Onset(ABC):
@@ -115,16 +121,50 @@ class FilteredWaveforms:
         return {key: block[i] for key, i in self.index.items()}
 
 
-class WaveformData:
-    """Minimal stand-in for ``quakemigrate.io.data.WaveformData`` (pre-processed data only)."""
+class Segment:
+    """One contiguous piece of a trace: ``offset`` samples after the container's ``starttime``."""
 
-    def __init__(self, channels: dict, starttime: float, sampling_rate: int):
+    __slots__ = ("offset", "data")
+
+    def __init__(self, offset: int, data):
+        self.offset, self.data = int(offset), np.asarray(data, dtype=np.double)
+
+    def __len__(self):
+        return len(self.data)
+
+
+def _as_segments(trace):
+    """A trace as a list of segments sorted by offset, perfectly contiguous neighbours merged."""
+    if isinstance(trace, Segment):
+        segs = [trace]
+    elif isinstance(trace, (list, tuple)) and (not trace or isinstance(trace[0], Segment)):
+        segs = sorted(trace, key=lambda g: g.offset)
+    else:
+        return [Segment(0, trace)]
+    merged = []
+    for g in segs:
+        if merged and merged[-1].offset + len(merged[-1]) == g.offset:
+            merged[-1] = Segment(merged[-1].offset, np.concatenate([merged[-1].data, g.data]))
+        else:
+            merged.append(g)
+    return merged
+
+
+class WaveformData:
+    """Minimal stand-in for ``quakemigrate.io.data.WaveformData`` (data at the onset's sampling rate)."""
+
+    def __init__(self, channels: dict, starttime: float, sampling_rate: int, endtime: float | None = None):
         self.channels = channels
         self.stations = list(channels.keys())
         self.starttime = starttime
         self.sampling_rate = sampling_rate
-        n = max((len(v) for comp in channels.values() for v in comp.values()), default=0)
-        self.endtime = starttime + (n - 1) / sampling_rate if n else starttime
+        if endtime is None:
+            n = 0
+            for comps in channels.values():
+                for tr in comps.values():
+                    n = max([n] + [g.offset + len(g) for g in _as_segments(tr)])
+            endtime = starttime + (n - 1) / sampling_rate if n else starttime
+        self.endtime = endtime
 
 
 class DataAvailabilityException(Exception):
@@ -162,6 +202,9 @@ class STALTAOnset(Onset):
             raise ValueError(f"unknown signal_transform {self.signal_transform!r}")
         self.min_onset_value = kwargs.get("min_onset_value", 0.4)
         self.all_channels = kwargs.get("all_channels", False)
+        self.channel_counts = kwargs.get("channel_counts", {"P": 1, "S": 2})  # stalta.py:322
+        self.allow_gaps = kwargs.get("allow_gaps", False)                      # stalta.py:326
+        self.full_timespan = kwargs.get("full_timespan", True)                 # stalta.py:327
         self.bandpass_filters = kwargs.get("bandpass_filters", None)
         if self.bandpass_filters is not None:
             from .preprocess import NyquistException
@@ -201,13 +244,35 @@ class STALTAOnset(Onset):
         return self.sta_lta_windows[phase][0] * self.sampling_rate / 2
 
     # -- the onset calculation ------------------------------------------------------------------
+    def _expected_samples(self, data) -> int:
+        """Samples a trace covering the container's timespan holds (io/data.py:612: timespan * sr + 1)."""
+        return int(round(float(data.endtime - data.starttime) * self.sampling_rate)) + 1
+
+    def _channel_ok(self, segs, n_expected) -> bool:
+        """One channel against the criteria of ``check_availability`` (io/data.py:585-633)."""
+        if not segs or any(len(g) == 0 for g in segs):
+            return False
+        if any(g.data.max() == g.data.min() for g in segs):          # flat-lined (:594-595)
+            return False
+        ends = [g.offset + len(g) for g in segs]
+        if any(b.offset < e for e, b in zip(ends[:-1], segs[1:])):   # overlaps (:597-599)
+            return False
+        if not self.allow_gaps and len(segs) > 1:                    # gaps (:601-604)
+            return False
+        if self.full_timespan and (len(segs) > 1 or len(segs[0]) < n_expected):   # (:611-621)
+            return False
+        return True
+
     def _plan(self, data):
         """
         Row order and availability exactly like stalta.py:389-470: phase-outer, station-inner,
-        key ``f"{station}_{phase}"``; a row is available when at least one (``all_channels``:
-        every) mapped component is present with the full length.
+        key ``f"{station}_{phase}"``.  A channel counts when it passes :meth:`_channel_ok`; a row is
+        available when at least one mapped component does (``all_channels``: every one of them, and
+        as many as ``channel_counts[phase]``, io/data.py:636-650).  The expected trace length comes
+        from the container's timespan, not from whichever trace happens to be seen first.
         """
-        n_total = None
+        n_expected = self._expected_samples(data)
+        strict = self.full_timespan and not self.allow_gaps
         availability, rows, chan_arrays = {}, [], []
         chan_index = {}
         per_phase = self.bandpass_filters is not None  # filtered traces are specific to a phase
@@ -217,27 +282,58 @@ class STALTAOnset(Onset):
             nsta = time2sample(stw, self.sampling_rate) + 1  # stalta.py:395-396
             nlta = time2sample(ltw, self.sampling_rate) + 1
             for station in data.stations:
-                have = [c for c in comps if c in data.channels.get(station, {})]
-                ok = len(have) == len(comps) if self.all_channels else len(have) > 0
-                if ok:
-                    lengths = {len(data.channels[station][c]) for c in have}
-                    n_here = lengths.pop() if len(lengths) == 1 else None
-                    ok = n_here is not None and (n_total is None or n_here == n_total)
-                    if ok and n_total is None:
-                        n_total = n_here
+                present = {c: _as_segments(data.channels[station][c])
+                           for c in comps if c in data.channels.get(station, {})}
+                good = {c: segs for c, segs in present.items() if self._channel_ok(segs, n_expected)}
+                if strict:  # a full-length trace must also start on the first sample
+                    good = {c: segs for c, segs in good.items()
+                            if segs[0].offset == 0 and len(segs[0]) == n_expected}
+                if self.all_channels:
+                    ok = len(present) > 0 and len(good) == len(present) == self.channel_counts.get(phase, len(comps))
+                else:
+                    ok = len(good) > 0
                 availability[f"{station}_{phase}"] = 1 if ok else 0
                 if not ok:
                     continue
                 idxs = []
-                for c in have:
+                for c, segs in good.items():
                     key = (station, c, phase) if per_phase else (station, c)
                     if key not in chan_index:
                         chan_index[key] = len(chan_arrays)
-                        chan_arrays.append(np.asarray(data.channels[station][c], dtype=np.double))
+                        chan_arrays.append(segs[0].data if strict else segs)
                     idxs.append(chan_index[key])
                 rows.append((station, phase, idxs, nsta, nlta))
         self._last_chan_index = chan_index
         return availability, rows, chan_arrays
+
+    def _assemble_gappy(self, chan_segments, chan_index, n_expected):
+        """
+        stalta.py:436-462 for ``allow_gaps`` / ``full_timespan=False``: every segment is
+        pre-processed on its own (the obspy calls of ``pre_process`` work trace by trace), tapered
+        once more (5 % cosine), then the segments of a channel are merged, gaps and the missing
+        start / end filled with ``sqrt(tiny)`` so that the energy trace stays positive.
+        Returns full-length float64 channel arrays ``(n_channels, n_expected)``.
+        """
+        from .preprocess import butter_sos, cosine_taper_window
+
+        tiny = np.sqrt(np.finfo(float).tiny)
+        phase_of = {i: (key[2] if len(key) == 3 else None) for key, i in chan_index.items()}
+        out = np.full((len(chan_segments), n_expected), tiny)
+        sos_cache = {}
+        for i, segs in enumerate(chan_segments):
+            phase = phase_of[i]
+            for g in segs:
+                x = g.data
+                if self.bandpass_filters is not None:
+                    if phase not in sos_cache:
+                        lowcut, highcut, corners = self.bandpass_filters[phase]
+                        sos_cache[phase] = butter_sos("bandpass", (lowcut, highcut), self.sampling_rate, corners)
+                    x = self.engine.preprocess(x[None, :], sos_cache[phase])[0]
+                x = x * cosine_taper_window(len(x), 0.05)
+                a, b = max(g.offset, 0), min(g.offset + len(x), n_expected)   # trim to the timespan (:454-460)
+                if b > a:
+                    out[i, a:b] = x[a - g.offset:b - g.offset]
+        return out
 
     def _filter_on_device(self, waveforms, chan_index):
         """``pre_process`` (stalta.py:203-209) per phase; returns the filtered DeviceWaveforms."""
@@ -277,9 +373,21 @@ class STALTAOnset(Onset):
         availability, rows, chan_arrays = self._plan(data)
         if sum(availability.values()) == 0:
             raise DataAvailabilityException
-        waveforms = np.stack(chan_arrays, axis=0)
+        gappy = self.allow_gaps or not self.full_timespan
+        if gappy:
+            waveforms = self._assemble_gappy(chan_arrays, self._last_chan_index, self._expected_samples(data))
+        else:
+            waveforms = np.stack(chan_arrays, axis=0)
         filtered_waveforms = data.channels
-        if self.bandpass_filters is not None:
+        if gappy and self.bandpass_filters is not None:
+            # already filtered segment by segment: only the onset stage is left
+            raw = self.engine.upload_waveforms(waveforms)
+            dev, onsets = self.engine.onsets_from_device_waveforms(
+                raw, [r[2] for r in rows], [r[3] for r in rows], [r[4] for r in rows],
+                position=self.position, transform=self.signal_transform,
+                min_onset_value=self.min_onset_value, return_onsets=True)
+            filtered_waveforms = FilteredWaveforms(raw, dict(self._last_chan_index))
+        elif self.bandpass_filters is not None:
             filtered = self._filter_on_device(waveforms, self._last_chan_index)
             dev, onsets = self.engine.onsets_from_device_waveforms(
                 filtered, [r[2] for r in rows], [r[3] for r in rows], [r[4] for r in rows],

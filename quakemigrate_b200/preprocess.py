@@ -25,7 +25,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["butter_sos", "pre_process", "decimate", "upsample", "NyquistException"]
+__all__ = ["butter_sos", "pre_process", "decimate", "upsample", "cosine_taper_window", "NyquistException"]
 
 
 class NyquistException(Exception):
@@ -119,6 +119,33 @@ def butter_sos(kind: str, freqs, df: float, corners: int) -> np.ndarray:
     for i, (zz, pp) in enumerate(sections):
         sos[i] = _section(zz, pp, k_z if i == 0 else 1.0)
     return sos
+
+
+def cosine_taper_window(npts: int, max_percentage: float = 0.05) -> np.ndarray:
+    """
+    The window ``Trace.taper(type="cosine", max_percentage=p)`` of obspy multiplies a trace by
+    (what stalta.py:207 and :448 apply).  obspy takes ``w = min(int(p * npts), npts // 2)`` samples
+    per side from ``cosine_taper(2 w + 1, p=1.0)`` (``2 w`` points when they span the whole trace):
+    a half cosine that is 0 on the first sample and reaches 1 on sample ``w - 1``; everything
+    between the two sides is 1.  Host form of the device taper in ``csrc/qmb_preprocess.cu`` (used
+    for the segments of gappy channels); the device taper is pinned end to end against obspy's own
+    output by tests/test_iceland_locate.py, this one against the device and the oracle.
+    """
+    npts = int(npts)
+    w = min(int(max_percentage * npts), npts // 2)
+    win = np.ones(npts)
+    if w > 0:
+        m = 2 * w if 2 * w == npts else 2 * w + 1      # length of the generating window
+        rise_end = max(m // 2 - 1, 1)                   # index where the rising half reaches 1 (>= 1)
+        fall_start = m - m // 2
+        if fall_start == m - 1:                         # degenerate one-interval falling half
+            fall_start -= 1
+        k = np.arange(w)
+        win[:w] = np.where(k <= rise_end, 0.5 * (1.0 - np.cos(np.pi * k / rise_end)), 1.0)
+        j = np.arange(m - w, m)                         # last w samples of the generating window
+        fall = 0.5 * (1.0 + np.cos(np.pi * (fall_start - j) / (m - 1 - fall_start)))
+        win[npts - w:] = np.where(j >= fall_start, fall, 1.0)
+    return win
 
 
 # ------------------------------------------------------------------------------------------------

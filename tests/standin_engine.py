@@ -117,6 +117,11 @@ class StandInEngine:
             out.a[out_chan0 + k] = t[::decimate]
         return (out, 0.0) if timing else out
 
+    def preprocess(self, waveforms, sos=None, detrend=True, taper_fraction=0.05, zerophase=True, decimate=1):
+        raw = self.upload_waveforms(waveforms)
+        return self.filter_waveforms(raw, sos, detrend=detrend, taper_fraction=taper_fraction,
+                                     zerophase=zerophase, decimate=decimate).fetch()
+
     # -- detect ------------------------------------------------------------------------------
     def detect_device(self, lut, onsets, fsmp, lsmp, available):
         n_samples = onsets.n_total - fsmp - lsmp
