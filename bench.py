@@ -75,6 +75,8 @@ def parse_args():
                     help="weak scaling: one workload-sized slab per GPU stacked along x "
                          "(default: strong, the FIXED workload grid sharded over the ranks)")
     ap.add_argument("--strong", action="store_true", help="(default; kept for round-1 command lines)")
+    ap.add_argument("--plane-slabs", action="store_true",
+                    help="strong scaling with whole x-planes per rank (round-1 sharding) instead of equal node ranges")
     ap.add_argument("--e2e-steps", type=int, default=5,
                     help="cap of the end-to-end loop (host buffers in and out); the device-timed loop runs --steps")
     ap.add_argument("--parity-windows", type=int, default=3)
@@ -353,16 +355,23 @@ def parity_and_cpu_baseline(args, cfg, tt_global, prob, onsets_lin, res):
 # ------------------------------------------------------------------------------------------------
 def run_ours(args, rank: int, world: int, local_rank: int, dist):
     from quakemigrate_b200.core import Engine
-    from quakemigrate_b200.sharding import slab_bounds
+    from quakemigrate_b200.sharding import balanced_range, slab_bounds
 
     base = syn.CONFIGS[args.workload]
     cfg = global_config(base, world, args.samples, args.weak)
+    nx, ny, nz = cfg.grid
+    plane = ny * nz
     if args.weak:
         x0, x1 = rank * base.grid[0], (rank + 1) * base.grid[0]
+        node_first, N_local = x0 * plane, (x1 - x0) * plane
+    elif args.plane_slabs:
+        x0, x1 = slab_bounds(nx, world, rank)
+        node_first, N_local = x0 * plane, (x1 - x0) * plane
     else:
-        x0, x1 = slab_bounds(cfg.grid[0], world, rank)
+        # equal shares of the C-order node list in whole z-columns: the cuts may fall inside an x-plane
+        node_first, N_local = balanced_range(nx, ny, nz, world, rank)
+        x0, x1 = node_first // plane, -(-(node_first + N_local) // plane)
     prob = syn.make_problem(cfg, with_waveforms=True, x_range=(x0, x1))
-    N_local = (x1 - x0) * cfg.grid[1] * cfg.grid[2]
     N_global, T, S = cfg.n_nodes, cfg.n_samples, cfg.n_rows
     P = prob.n_total
 
@@ -377,7 +386,9 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
         dist.broadcast_object_list(ids, src=0, group=CTRL_GROUP)
         eng.init_comm(ids[0], world, rank)
 
-    lut = eng.upload_lut(prob.traveltimes, node_offset=x0 * cfg.grid[1] * cfg.grid[2], n_nodes_global=N_global)
+    rows = prob.traveltimes.reshape(-1, S)[node_first - x0 * plane: node_first - x0 * plane + N_local]
+    lut = eng.upload_lut_range(rows, ny, nz, node_first, N_global)
+    del rows
     dev_on, onsets_lin = eng.onsets_from_waveforms(prob.waveforms, prob.row_channels, prob.nsta, prob.nlta,
                                                    position=cfg.position, return_onsets=True)
     info = lut.info()
@@ -458,10 +469,12 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {
             "workload": f"{cfg.name}: {cfg.grid[0]}x{cfg.grid[1]}x{cfg.grid[2]} grid "
-                        f"({x1 - x0}x{cfg.grid[1]}x{cfg.grid[2]} x-slab on rank {rank}), {S} onset rows, "
+                        f"(nodes [{node_first}, {node_first + N_local}) on rank {rank}), {S} onset rows, "
                         f"{T} samples @ {cfg.sampling_rate} Hz, {cfg.position} STA/LTA, detect() scan",
             "n_nodes": N_global, "n_rows": S, "n_samples": T, "fsmp": prob.fsmp, "lsmp": prob.lsmp,
-            "parallelism": f"node-slab x{world} ({'one workload-sized slab per GPU' if args.weak else 'fixed grid sharded by x-planes'})",
+            "parallelism": f"node-slab x{world} (" + ("one workload-sized slab per GPU" if args.weak else
+                           "fixed grid, x-plane slabs" if args.plane_slabs else
+                           "fixed grid, equal contiguous node ranges in whole z-columns") + ")",
             "cache": "L2 flushed (256 MiB memset) before every timed step",
             "nodes_per_tile": info["nodes_per_tile"], "max_tile_span": info["max_tile_span"],
             "variant": info["variant"], "duplicate_fraction": round(info["duplicate_fraction"], 4),
@@ -509,7 +522,7 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
         line["stages"] = {"preprocess": preprocess_stage(eng, cfg, prob, args, peak, peak_src)}
     if rank == 0 and not args.no_cpu_baseline:
         # the GLOBAL table on rank 0's host (the reference needs all nodes)
-        tt_global = prob.traveltimes if world == 1 else syn.make_traveltimes(cfg)[0]
+        tt_global = prob.traveltimes if (x0 == 0 and x1 == nx) else syn.make_traveltimes(cfg)[0]
         line["parity_vs_reference_sample"], line["cpu_baseline"] = parity_and_cpu_baseline(
             args, cfg, tt_global, prob, onsets_lin, res)
         del tt_global

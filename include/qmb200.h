@@ -170,6 +170,12 @@ int qmb_comm_destroy(qmb_ctx_t ctx);
  * (migratelib.c:55).  Upload once per availability pattern; reuse across calls. */
 int qmb_lut_upload(qmb_ctx_t ctx, const int32_t *lut, int32_t nx_local, int32_t ny, int32_t nz,
                    int32_t n_rows, int64_t node_offset, int64_t n_nodes_global, qmb_lut_t *out);
+/* The same for a slab given as a range of the C-order node list, [node_first, node_first +
+ * n_nodes_local): whole z-columns (multiples of nz), but free to begin and end inside an x-plane, so
+ * that G ranks can hold N / G nodes each whatever nx is.  `lut` holds the rows of exactly that range,
+ * (n_nodes_local, n_rows). */
+int qmb_lut_upload_range(qmb_ctx_t ctx, const int32_t *lut, int32_t ny, int32_t nz, int32_t n_rows,
+                         int64_t node_first, int64_t n_nodes_local, int64_t n_nodes_global, qmb_lut_t *out);
 int qmb_lut_free(qmb_lut_t lut);
 
 /* LUT.serve_traveltimes on the device (quakemigrate/lut/lut.py:502-538).  Upload every

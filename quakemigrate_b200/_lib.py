@@ -98,6 +98,8 @@ SIGNATURES = {
     "qmb_comm_destroy": (ctypes.c_int, [c_void_p]),
     "qmb_lut_upload": (ctypes.c_int, [c_void_p, c_i32Pt, c_int32, c_int32, c_int32, c_int32, c_int64,
                                       c_int64, ctypes.POINTER(c_void_p)]),
+    "qmb_lut_upload_range": (ctypes.c_int, [c_void_p, c_i32Pt, c_int32, c_int32, c_int32, c_int64, c_int64, c_int64,
+                                            ctypes.POINTER(c_void_p)]),
     "qmb_lut_free": (ctypes.c_int, [c_void_p]),
     "qmb_ttgrids_upload": (ctypes.c_int, [c_void_p, c_dPt, c_int32, c_int32, c_int32, c_int32,
                                           ctypes.POINTER(c_void_p)]),

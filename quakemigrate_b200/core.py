@@ -422,6 +422,22 @@ class Engine:
                                             ctypes.byref(h)))
         return DeviceLUT(self, h, tt.shape, int(node_offset), n_glob)
 
+    def upload_lut_range(self, rows: np.ndarray, ny: int, nz: int, node_first: int,
+                         n_nodes_global: int) -> DeviceLUT:
+        """
+        A slab given as a contiguous range of the C-order node list: ``rows`` is int32
+        ``(n_nodes_local, n_rows)`` = ``traveltimes.reshape(-1, n_rows)[node_first : node_first +
+        n_nodes_local]``; both ends must fall on whole z-columns (multiples of ``nz``) but may lie
+        inside an x-plane -- see :func:`quakemigrate_b200.sharding.balanced_range`.
+        """
+        tt = np.ascontiguousarray(rows, dtype=np.int32)
+        if tt.ndim != 2:
+            raise ValueError("rows must have shape (n_nodes_local, n_onsets)")
+        h = ctypes.c_void_p()
+        _lib.check(self._lib.qmb_lut_upload_range(self._h, tt, int(ny), int(nz), tt.shape[1], int(node_first),
+                                                  tt.shape[0], int(n_nodes_global), ctypes.byref(h)))
+        return DeviceLUT(self, h, tt.shape, int(node_first), int(n_nodes_global))
+
     def upload_traveltime_grids(self, grids: np.ndarray) -> "DeviceGrids":
         """``grids``: float64 (n_grids, nx, ny, nz) travel times in seconds, kept on the device."""
         g = np.ascontiguousarray(grids, dtype=np.double)

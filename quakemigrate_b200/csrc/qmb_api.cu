@@ -298,25 +298,10 @@ int qmb_nccl_allreduce_sum_f64(qmb_ctx *ctx, double *buf, size_t count) {
 // ---------------------------------------------------------------------------------------------
 // travel-time table
 // ---------------------------------------------------------------------------------------------
-extern "C" int qmb_lut_upload(qmb_ctx_t ctx, const int32_t *lut, int32_t nx_local, int32_t ny, int32_t nz,
-                              int32_t n_rows, int64_t node_offset, int64_t n_nodes_global, qmb_lut_t *out) {
-  if (!ctx || !lut || !out) QMB_FAIL(QMB_ERR_ARG, "null argument");
-  *out = nullptr;
-  if (nx_local <= 0 || ny <= 0 || nz <= 0 || n_rows <= 0) QMB_FAIL(QMB_ERR_ARG, "empty travel-time table");
-  const int64_t n_local = (int64_t)nx_local * ny * nz;
-  if (n_nodes_global <= 0) n_nodes_global = n_local;
-  if (node_offset < 0 || node_offset + n_local > n_nodes_global)
-    QMB_FAIL(QMB_ERR_ARG, "node slab [%lld, %lld) outside the global grid of %lld nodes", (long long)node_offset,
-             (long long)(node_offset + n_local), (long long)n_nodes_global);
-  if (n_nodes_global >= 0xFFFFFFFFLL) QMB_FAIL(QMB_ERR_UNSUPPORTED, "more than 2^32-2 nodes");
-  QMB_CUDA(cudaSetDevice(ctx->device));
-  qmb_lut *L = new qmb_lut();
-  L->ctx = ctx;
-  L->device = ctx->device;
-  L->nxl = nx_local; L->ny = ny; L->nz = nz; L->S = n_rows;
-  L->node_offset = node_offset; L->n_global = n_nodes_global; L->n_local = n_local;
+// shared by the two upload forms: raw rows of the slab -> device, tile, free the raw copy
+static int lut_upload_common(qmb_ctx_t ctx, qmb_lut *L, const int32_t *lut, qmb_lut_t *out) {
   int32_t *d_raw = nullptr;
-  const size_t raw_bytes = (size_t)n_local * n_rows * sizeof(int32_t);
+  const size_t raw_bytes = (size_t)L->n_local * L->S * sizeof(int32_t);
   cudaError_t e = cudaMalloc((void **)&d_raw, raw_bytes);
   if (e != cudaSuccess) {
     delete L;
@@ -337,6 +322,56 @@ extern "C" int qmb_lut_upload(qmb_ctx_t ctx, const int32_t *lut, int32_t nx_loca
   }
   *out = L;
   return QMB_OK;
+}
+
+extern "C" int qmb_lut_upload(qmb_ctx_t ctx, const int32_t *lut, int32_t nx_local, int32_t ny, int32_t nz,
+                              int32_t n_rows, int64_t node_offset, int64_t n_nodes_global, qmb_lut_t *out) {
+  if (!ctx || !lut || !out) QMB_FAIL(QMB_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (nx_local <= 0 || ny <= 0 || nz <= 0 || n_rows <= 0) QMB_FAIL(QMB_ERR_ARG, "empty travel-time table");
+  const int64_t n_local = (int64_t)nx_local * ny * nz;
+  if (n_nodes_global <= 0) n_nodes_global = n_local;
+  if (node_offset < 0 || node_offset + n_local > n_nodes_global)
+    QMB_FAIL(QMB_ERR_ARG, "node slab [%lld, %lld) outside the global grid of %lld nodes", (long long)node_offset,
+             (long long)(node_offset + n_local), (long long)n_nodes_global);
+  if (n_nodes_global >= 0xFFFFFFFFLL) QMB_FAIL(QMB_ERR_UNSUPPORTED, "more than 2^32-2 nodes");
+  QMB_CUDA(cudaSetDevice(ctx->device));
+  qmb_lut *L = new qmb_lut();
+  L->ctx = ctx;
+  L->device = ctx->device;
+  L->nxl = nx_local; L->ny = ny; L->nz = nz; L->S = n_rows;
+  L->node_offset = node_offset; L->n_global = n_nodes_global; L->n_local = n_local;
+  return lut_upload_common(ctx, L, lut, out);
+}
+
+// A slab given as a range of the C-order node list: [node_first, node_first + n_nodes_local), whole
+// z-columns (both multiples of nz).  It may begin and end inside an x-plane, so that G ranks can
+// hold N / G nodes each whatever nx is (x-plane slabs of a 201-plane grid over 8 ranks are 26 or 25
+// planes: 3.5 % imbalance).
+extern "C" int qmb_lut_upload_range(qmb_ctx_t ctx, const int32_t *lut, int32_t ny, int32_t nz, int32_t n_rows,
+                                    int64_t node_first, int64_t n_nodes_local, int64_t n_nodes_global,
+                                    qmb_lut_t *out) {
+  if (!ctx || !lut || !out) QMB_FAIL(QMB_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (ny <= 0 || nz <= 0 || n_rows <= 0 || n_nodes_local <= 0) QMB_FAIL(QMB_ERR_ARG, "empty travel-time table");
+  const int64_t plane = (int64_t)ny * nz;
+  if (node_first < 0 || node_first % nz != 0 || n_nodes_local % nz != 0)
+    QMB_FAIL(QMB_ERR_ARG, "a node range must consist of whole z-columns (multiples of nz = %d)", nz);
+  if (n_nodes_global <= 0 || n_nodes_global % plane != 0 || node_first + n_nodes_local > n_nodes_global)
+    QMB_FAIL(QMB_ERR_ARG, "node range [%lld, %lld) outside the global grid of %lld nodes", (long long)node_first,
+             (long long)(node_first + n_nodes_local), (long long)n_nodes_global);
+  if (n_nodes_global >= 0xFFFFFFFFLL) QMB_FAIL(QMB_ERR_UNSUPPORTED, "more than 2^32-2 nodes");
+  QMB_CUDA(cudaSetDevice(ctx->device));
+  const int64_t last = node_first + n_nodes_local;
+  const int64_t xa = node_first / plane, xb = (last + plane - 1) / plane;
+  qmb_lut *L = new qmb_lut();
+  L->ctx = ctx;
+  L->device = ctx->device;
+  L->nxl = (int32_t)(xb - xa); L->ny = ny; L->nz = nz; L->S = n_rows;
+  L->y_first = (int32_t)((node_first % plane) / nz);
+  L->y_last = (int32_t)((last % plane) / nz);
+  L->node_offset = node_first; L->n_global = n_nodes_global; L->n_local = n_nodes_local;
+  return lut_upload_common(ctx, L, lut, out);
 }
 
 // --- serving from device-resident float64 grids (LUT.serve_traveltimes on the device) ------------
@@ -706,6 +741,8 @@ extern "C" int qmb_locate_window_device(qmb_ctx_t ctx, qmb_lut_t lut, qmb_onsets
   *coa_map = nullptr;
   if (lut->ctx != ctx || onsets->ctx != ctx) QMB_FAIL(QMB_ERR_ARG, "handles belong to a different context");
   QMB_CUDA(cudaSetDevice(ctx->device));
+  if (lut->y_first || lut->y_last)
+    QMB_FAIL(QMB_ERR_UNSUPPORTED, "a device map needs a slab of whole x-planes (this table is a ragged node range)");
   qmb_map3d *m = nullptr;
   QMB_TRY(qmb_map3d_new(ctx, lut->nxl, lut->ny, lut->nz, &m));
   const int rc = qmb_window_run(ctx, lut, onsets, fsmp, lsmp, available, win0, win1, m->v.p, nullptr, 0);

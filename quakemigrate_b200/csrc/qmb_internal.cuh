@@ -148,6 +148,9 @@ struct qmb_lut {
   qmb_ctx *ctx = nullptr;
   int device = 0;  // copied from ctx: handles may outlive their context
   int32_t nxl = 0, ny = 0, nz = 0, S = 0, Spad = 0, chunk_rows = QMB_DEFAULT_CHUNK_ROWS;
+  // a slab is a contiguous range of the C-order node list in whole z-columns: it covers nxl x-planes,
+  // skips the first y_first rows of the first one and keeps only y_last rows of the last (0: all)
+  int32_t y_first = 0, y_last = 0;
   int64_t node_offset = 0, n_global = 0, n_local = 0;
   QmbVariant v = QMB_VARIANTS[QMB_DEFAULT_VARIANT];  // variant this table was tiled for
   int tx = 4, ty = 4, tz = 4, NB = 64;

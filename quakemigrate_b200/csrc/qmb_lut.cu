@@ -33,6 +33,8 @@ struct LutTileParams {
   const int *boxes;    // [n_tiles][9]: origin x0,y0,z0; tile shape sx,sy,sz; region end x1,y1,z1
   uint32_t *slotmap;   // [n_local]: tile * NB + slot of every node
   long long node_offset, n_valid;
+  long long first;     // flat index (inside the covering box) of the slab's first node: a slab may start
+                       // and end in the middle of an x-plane (whole z-columns), see qmb_lut_upload_range
   uint16_t *tau16;
   int32_t *tmin;
   uint16_t *span;
@@ -58,10 +60,11 @@ __global__ void __launch_bounds__(LT_THREADS) k_lut_tile(LutTileParams p) {
     // slots outside the tile's region (or the grid) are padding; they replicate the nearest
     // in-region node so that they do not widen the tile's travel-time range
     const int cx = min(ix, bx[6] - 1), cy = min(iy, bx[7] - 1), cz = min(iz, bx[8] - 1);
-    long long local = ((long long)cx * p.ny + cy) * p.nz + cz;
-    const long long flat = ((long long)ix * p.ny + iy) * p.nz + iz;
-    const bool valid = ix < bx[6] && iy < bx[7] && iz < bx[8] && flat < p.n_valid;
+    long long local = ((long long)cx * p.ny + cy) * p.nz + cz - p.first;
+    const long long flat = ((long long)ix * p.ny + iy) * p.nz + iz - p.first;
+    const bool valid = ix < bx[6] && iy < bx[7] && iz < bx[8] && flat >= 0 && flat < p.n_valid;
     if (local >= p.n_valid) local = p.n_valid - 1;  // ragged last x-plane of a pseudo-grid
+    if (local < 0) local = 0;
     s_node[tid] = local;
     p.nodeidx[(size_t)j * p.NB + tid] = valid ? (uint32_t)(p.node_offset + flat) : 0xFFFFFFFFu;
     if (valid) p.slotmap[flat] = (uint32_t)j * (uint32_t)p.NB + (uint32_t)tid;
@@ -208,20 +211,43 @@ static int lut_build_variant(qmb_ctx *ctx, qmb_lut *L, const int32_t *d_raw, con
   L->tz = L->v.tz;
   L->NB = L->tx * L->ty * L->tz;
   std::vector<int> boxes;
-  {
-    const int Mx = (L->nxl / L->tx) * L->tx, My = (L->ny / L->ty) * L->ty, Mz = (L->nz / L->tz) * L->tz;
+  // bulk tiles of the variant's shape + up to three remainder slabs per box; a slab that starts /
+  // ends inside an x-plane is three boxes: the partial first plane, the whole planes, the partial
+  // last plane
+  auto tile_box = [&](const Region &b) {
+    const int ex = b.x1 - b.x0, ey = b.y1 - b.y0, ez = b.z1 - b.z0;
+    if (ex <= 0 || ey <= 0 || ez <= 0) return;
+    const int Mx = (ex / L->tx) * L->tx, My = (ey / L->ty) * L->ty, Mz = (ez / L->tz) * L->tz;
     int sx, sy, sz;
-    if (Mx > 0 && My > 0 && Mz > 0) tile_region({0, 0, 0, Mx, My, Mz}, L->tx, L->ty, L->tz, boxes);
+    if (Mx > 0 && My > 0 && Mz > 0)
+      tile_region({b.x0, b.y0, b.z0, b.x0 + Mx, b.y0 + My, b.z0 + Mz}, L->tx, L->ty, L->tz, boxes);
     const Region rem[3] = {
-        {Mx, 0, 0, L->nxl, L->ny, L->nz},                       // x remainder (everything if Mx == 0)
-        {0, My, 0, Mx, L->ny, L->nz},                           // y remainder
-        {0, 0, (My > 0 ? Mz : 0), Mx, My, L->nz},               // z remainder
+        {b.x0 + Mx, b.y0, b.z0, b.x1, b.y1, b.z1},                            // x remainder (everything if Mx == 0)
+        {b.x0, b.y0 + My, b.z0, b.x0 + Mx, b.y1, b.z1},                       // y remainder
+        {b.x0, b.y0, b.z0 + (My > 0 ? Mz : 0), b.x0 + Mx, b.y0 + My, b.z1},   // z remainder
     };
     for (const Region &r : rem) {
       if (r.x1 <= r.x0 || r.y1 <= r.y0 || r.z1 <= r.z0) continue;
       best_shape(L->NB, r.x1 - r.x0, r.y1 - r.y0, r.z1 - r.z0, sx, sy, sz);
       tile_region(r, sx, sy, sz, boxes);
     }
+  };
+  {
+    int xs = 0, xe = L->nxl;
+    if (L->nxl == 1 && (L->y_first > 0 || L->y_last > 0)) {
+      tile_box({0, L->y_first, 0, 1, L->y_last > 0 ? L->y_last : L->ny, L->nz});
+      xs = xe = 0;
+    } else {
+      if (L->y_first > 0) {
+        tile_box({0, L->y_first, 0, 1, L->ny, L->nz});
+        xs = 1;
+      }
+      if (L->y_last > 0) {
+        tile_box({L->nxl - 1, 0, 0, L->nxl, L->y_last, L->nz});
+        xe = L->nxl - 1;
+      }
+    }
+    tile_box({xs, 0, 0, xe, L->ny, L->nz});
   }
   const long long nt = (long long)(boxes.size() / 9);
   if (nt > 0x7fffffffLL / 128) QMB_FAIL(QMB_ERR_UNSUPPORTED, "too many node tiles (%lld)", nt);
@@ -252,6 +278,7 @@ static int lut_build_variant(qmb_ctx *ctx, qmb_lut *L, const int32_t *d_raw, con
   p.slotmap = L->slotmap.p;
   p.node_offset = L->node_offset;
   p.n_valid = L->n_local;
+  p.first = (long long)L->y_first * L->nz;
   p.tau16 = L->tau16.p; p.tmin = L->tmin.p; p.span = L->span.p; p.nodeidx = L->nodeidx.p;
   p.stats = d_stats;
   p.NPW = L->v.NPW;

@@ -25,7 +25,7 @@ import numpy as np
 from oracle import qm_oracle as O
 from quakemigrate_b200 import synthetic as syn
 from quakemigrate_b200.core import Engine
-from quakemigrate_b200.sharding import shard_traveltimes
+from quakemigrate_b200.sharding import shard_traveltimes, shard_traveltimes_balanced
 
 rank, world, idfile = int(sys.argv[1]), int(sys.argv[2]), pathlib.Path(sys.argv[3])
 eng = Engine(rank)
@@ -55,10 +55,11 @@ for case, (grid, S, T, fsmp, lsmp, floor) in enumerate([((9, 6, 5), 6, 300, 5, 3
 
 # a longer scan: 16-bit rows with the cross-rank verification of the node sums, spot-checked
 # against the fused oracle; then adversarial rows that must make EVERY rank fall back together
-cfg = syn.CONFIGS["cfg2"].scaled(grid=(30, 24, 14), n_samples=4200, n_rows=12, name="mr")
+cfg = syn.CONFIGS["cfg2"].scaled(grid=(29, 24, 14), n_samples=4200, n_rows=12, name="mr")
 prob = syn.make_problem(cfg)
-slab, off, n_glob = shard_traveltimes(prob.traveltimes, world, rank)
-lut = eng.upload_lut(slab, node_offset=off, n_nodes_global=n_glob)
+# equal node ranges: with 29 x-planes over 2 ranks the cut falls in the middle of plane 14
+rows, off, n_glob = shard_traveltimes_balanced(prob.traveltimes, world, rank)
+lut = eng.upload_lut_range(rows, cfg.grid[1], cfg.grid[2], off, n_glob)
 dev, onsets = eng.onsets_from_waveforms(prob.waveforms, prob.row_channels, prob.nsta, prob.nlta,
                                         position=cfg.position, return_onsets=True)
 eng.detect_device(lut, dev, prob.fsmp, prob.lsmp, cfg.n_rows)

@@ -104,9 +104,10 @@ def test_marginal_window_indices():
 def test_stalta_onset_plan_orders_rows_like_the_reference():
     from quakemigrate_b200.onsets import STALTAOnset, WaveformData
     n = 300
-    ch = {"A": {"Z": np.zeros(n), "N": np.zeros(n), "E": np.zeros(n)},
-          "B": {"Z": np.zeros(n)},                                  # no horizontals -> no S row
-          "C": {"N": np.zeros(n), "E": np.zeros(n)}}                # no vertical -> no P row
+    tr = lambda k: np.sin(np.arange(n) * (0.1 + 0.01 * k))          # noqa: E731  (flat-lined traces are dropped)
+    ch = {"A": {"Z": tr(0), "N": tr(1), "E": tr(2)},
+          "B": {"Z": tr(3)},                                        # no horizontals -> no S row
+          "C": {"N": tr(4), "E": tr(5)}}                            # no vertical -> no P row
     on = STALTAOnset(sampling_rate=100)
     avail, rows, chans = on._plan(WaveformData(ch, 0.0, 100))
     assert list(avail.items()) == [("A_P", 1), ("B_P", 1), ("C_P", 0), ("A_S", 1), ("B_S", 0), ("C_S", 1)]
@@ -189,3 +190,22 @@ def test_lut_decimate_matches_reference_slicing():
     assert dec2.serve_traveltimes(50).shape == (3, 2, 2, 6)
     lut.decimate([2, 2, 2], inplace=True)
     assert list(lut.node_count) == [6, 4, 4] and lut["S2"]["P"].shape == (6, 4, 4)
+
+
+def test_balanced_ranges_partition_the_node_list():
+    """sharding.balanced_range: contiguous, disjoint, covering, whole z-columns, sizes within one column."""
+    from quakemigrate_b200.sharding import balanced_range, shard_traveltimes_balanced
+    for (nx, ny, nz), world in (((201, 201, 101), 8), ((301, 301, 151), 8), ((7, 5, 3), 4), ((3, 3, 2), 9)):
+        end, sizes = 0, []
+        for r in range(world):
+            first, count = balanced_range(nx, ny, nz, world, r)
+            assert first == end and first % nz == 0 and count % nz == 0 and count > 0
+            end = first + count
+            sizes.append(count)
+        assert end == nx * ny * nz and max(sizes) - min(sizes) <= nz
+    tt = np.arange(4 * 3 * 2 * 5, dtype=np.int32).reshape(4, 3, 2, 5)
+    got = [shard_traveltimes_balanced(tt, 5, r) for r in range(5)]
+    assert np.array_equal(np.concatenate([g[0] for g in got]), tt.reshape(-1, 5))
+    assert [g[1] for g in got] == [0, 6, 12, 16, 20] and all(g[2] == 24 for g in got)
+    with pytest.raises(ValueError):
+        balanced_range(2, 2, 3, 5, 0)
