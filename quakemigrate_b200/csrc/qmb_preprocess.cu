@@ -26,6 +26,7 @@
 // sample for a zero-phase filter; the sections' arithmetic (10 flops per section and sample,
 // twice) hides under it.
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -332,6 +333,165 @@ __global__ void __launch_bounds__(PP_TPB) k_sos_apply(PreParams p) {
   }
 }
 
+// ---- single pass per direction ---------------------------------------------------------------------
+// One kernel does what k_sos_state + k_sos_carry + k_sos_apply do, reading every sample once and
+// writing it once (16 bytes per sample and direction instead of 24):
+//   1. the tile is staged in shared memory and every chunk is filtered IN PLACE from a zero state
+//      (zero-state response y0, chunk end states);
+//   2. the in-tile scan turns the end states into chunk-start states relative to the tile start;
+//   3. the state at the tile start comes from the predecessors of the same trace by a decoupled
+//      look-back: every tile publishes its aggregate (end state from a zero start) as soon as it has
+//      it, and its inclusive end state once it knows its own start; a tile walks back until it meets
+//      an inclusive state and replays  in <- M^256 in + z  forward from there (tiles are handed out
+//      in launch order by a ticket, so every predecessor is running or done);
+//   4. the filter is linear: the true output is y0 plus the zero-input response of the cascade to
+//      the chunk's true start state, out[k] = y0[k] + sum_d resp[d][k] * state[d] -- D multiply-adds
+//      per sample, independent across samples, instead of a second serial pass of the cascade.
+// Rounding differs from scipy's sosfilt at the 1e-15 level of the trace's peak (the same level as
+// the three-kernel form, whose re-associated state propagation this shares).
+struct FusedScratch {
+  int *ticket;    // [1] next tile to hand out, followed by
+  int *flags;     // [n_sel * ntiles]  0: nothing, 1: aggregate published, 2: inclusive published
+  double *desc;   // [n_sel * ntiles][2][D]: aggregate, inclusive end state
+  const double *resp;  // [D][PP_L] zero-input response of the cascade output to unit start states
+};
+
+template <int NSEC, bool REV>
+__global__ void __launch_bounds__(PP_TPB) k_sos_fused(PreParams p, FusedScratch f) {
+  constexpr int D = 2 * NSEC;
+  extern __shared__ double sm[];
+  double *tile = sm;                            // PP_TPB * (PP_L + 1)
+  double *sv = tile + PP_TPB * (PP_L + 1);      // PP_TPB * D: scan buffer, then true chunk-start states
+  double *tin_s = sv + PP_TPB * D;              // D
+  double *R = tin_s + D;                        // D * PP_L
+  __shared__ int s_ticket;
+  const int t = threadIdx.x;
+  if (t == 0) s_ticket = atomicAdd(f.ticket, 1);
+  for (int i = t; i < D * PP_L; i += PP_TPB) R[i] = f.resp[i];
+  __syncthreads();
+  const int T = s_ticket % p.ntiles, s = s_ticket / p.ntiles;
+  load_tile<REV>(p, tile, T, s);
+  __syncthreads();
+  // 1. zero-state response in place
+  double st[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) st[d] = 0.0;
+  double *my = tile + t * (PP_L + 1);
+#pragma unroll 4
+  for (int k = 0; k < PP_L; ++k) my[k] = cascade_step<NSEC>(p.coef, st, my[k]);
+#pragma unroll
+  for (int d = 0; d < D; ++d) sv[t * D + d] = st[d];
+  // 2. inclusive scan over the chunks of the tile
+  for (int o = 1; o < PP_TPB; o <<= 1) {
+    __syncthreads();
+    double add[D];
+    if (t >= o) {
+      const double *M = p.mpow + (size_t)o * D * D;
+      const double *prev = sv + (t - o) * D;
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) acc += M[i * D + j] * prev[j];
+        add[i] = acc;
+      }
+    }
+    __syncthreads();
+    if (t >= o) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        st[i] += add[i];
+        sv[t * D + i] = st[i];
+      }
+    }
+  }
+  __syncthreads();
+  double c0[D];  // state at the start of this chunk, given a zero state at the start of the tile
+#pragma unroll
+  for (int d = 0; d < D; ++d) c0[d] = t ? sv[(t - 1) * D + d] : 0.0;
+  // 3. look-back (the thread that holds the tile aggregate)
+  if (t == PP_TPB - 1) {
+    const size_t me = (size_t)s * p.ntiles + T;
+    double *mine = f.desc + me * 2 * D;
+    const double *P = p.mpow + (size_t)PP_TPB * D * D;
+    volatile int *flags = f.flags;
+    double in[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) in[d] = 0.0;
+    if (T > 0) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) mine[d] = st[d];
+      __threadfence();
+      flags[me] = 1;
+      int j = T - 1;
+      int fl;
+      for (;;) {  // walk back to the nearest tile whose inclusive state is known (tile 0 always gets there)
+        while ((fl = flags[(size_t)s * p.ntiles + j]) == 0) {
+        }
+        if (fl == 2 || j == 0) break;
+        --j;
+      }
+      __threadfence();
+      if (fl == 2) {
+        const double *e = f.desc + ((size_t)s * p.ntiles + j) * 2 * D + D;
+#pragma unroll
+        for (int d = 0; d < D; ++d) in[d] = __ldcg(e + d);
+        ++j;
+      }
+      for (; j < T; ++j) {  // in <- P in + z_j
+        const double *z = f.desc + ((size_t)s * p.ntiles + j) * 2 * D;
+        double nx[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          double acc = __ldcg(z + i);
+#pragma unroll
+          for (int q = 0; q < D; ++q) acc += P[i * D + q] * in[q];
+          nx[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) in[i] = nx[i];
+      }
+    }
+    // inclusive end state of this tile: P in + z
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      double acc = st[i];
+#pragma unroll
+      for (int q = 0; q < D; ++q) acc += P[i * D + q] * in[q];
+      mine[D + i] = acc;
+    }
+    __threadfence();
+    flags[me] = 2;
+#pragma unroll
+    for (int d = 0; d < D; ++d) tin_s[d] = in[d];
+  }
+  __syncthreads();
+  // 4. true start state of every chunk, then the zero-input correction, coalesced
+  {
+    const double *M = p.mpow + (size_t)t * D * D;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      double acc = c0[i];
+#pragma unroll
+      for (int j = 0; j < D; ++j) acc += M[i * D + j] * tin_s[j];
+      sv[t * D + i] = acc;
+    }
+  }
+  __syncthreads();
+  double *y = p.y + (size_t)(p.chan_out0 + s) * p.y_stride;
+  for (int k = t; k < PP_TILE; k += PP_TPB) {
+    const long long q = (long long)T * PP_TILE + k;
+    if (q >= p.n) break;
+    const int c = k / PP_L, r = k % PP_L;
+    double v = tile[k + c];
+#pragma unroll
+    for (int d = 0; d < D; ++d) v += R[d * PP_L + r] * sv[c * D + d];
+    const long long i = REV ? p.n - 1 - q : q;
+    if (p.decimate <= 1) y[i] = v;
+    else if (i % p.decimate == 0) y[i / p.decimate] = v;
+  }
+}
+
 // detrend + taper only (no filter sections)
 __global__ void __launch_bounds__(256) k_pre_only(PreParams p) {
   const int s = blockIdx.y;
@@ -365,6 +525,55 @@ void chunk_transition(const double *coef, int nsec, int steps, std::vector<doubl
     }
     for (int i = 0; i < D; ++i) M[(size_t)i * D + j] = s[i];
   }
+}
+
+// resp[d][k] = output of the cascade at step k of a zero-input run started from unit state d
+void zero_input_response(const double *coef, int nsec, int steps, std::vector<double> &R) {
+  const int D = 2 * nsec;
+  R.assign((size_t)D * steps, 0.0);
+  std::vector<double> s(D);
+  for (int j = 0; j < D; ++j) {
+    for (int d = 0; d < D; ++d) s[d] = d == j ? 1.0 : 0.0;
+    for (int k = 0; k < steps; ++k) {
+      double x = 0.0;
+      for (int q = 0; q < nsec; ++q) {
+        const double *c = coef + 5 * q;
+        const double y = c[0] * x + s[2 * q];
+        s[2 * q] = c[1] * x - c[3] * y + s[2 * q + 1];
+        s[2 * q + 1] = c[2] * x - c[4] * y;
+        x = y;
+      }
+      R[(size_t)j * steps + k] = x;
+    }
+  }
+}
+
+template <int NSEC>
+int run_pass_fused(qmb_ctx *ctx, PreParams &p, const FusedScratch &f, bool rev) {
+  constexpr int D = 2 * NSEC;
+  const size_t smem = (size_t)(PP_TPB * (PP_L + 1) + PP_TPB * D + D + D * PP_L) * sizeof(double);
+  const unsigned n_ctas = (unsigned)p.ntiles * (unsigned)p.n_sel;
+  QMB_CUDA(cudaMemsetAsync(f.ticket, 0, (size_t)(1 + (size_t)p.ntiles * p.n_sel) * sizeof(int), ctx->stream));
+  if (rev) {
+    QMB_CUDA(cudaFuncSetAttribute(k_sos_fused<NSEC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_sos_fused<NSEC, true><<<n_ctas, PP_TPB, smem, ctx->stream>>>(p, f);
+  } else {
+    QMB_CUDA(cudaFuncSetAttribute(k_sos_fused<NSEC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_sos_fused<NSEC, false><<<n_ctas, PP_TPB, smem, ctx->stream>>>(p, f);
+  }
+  QMB_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return QMB_OK;
+}
+
+int run_pass_fused_n(qmb_ctx *ctx, int nsec, PreParams &p, const FusedScratch &f, bool rev) {
+  switch (nsec) {
+    case 1: return run_pass_fused<1>(ctx, p, f, rev);
+    case 2: return run_pass_fused<2>(ctx, p, f, rev);
+    case 3: return run_pass_fused<3>(ctx, p, f, rev);
+    case 4: return run_pass_fused<4>(ctx, p, f, rev);
+  }
+  QMB_FAIL(QMB_ERR_UNSUPPORTED, "filters with %d second-order sections are not built (1..%d)", nsec, PP_MAX_SEC);
 }
 
 template <int NSEC>
@@ -442,13 +651,28 @@ int qmb_preprocess_device(qmb_ctx *ctx, const double *d_x, int64_t x_stride, con
   const size_t n_chunk = (size_t)n_sel * p.ntiles * PP_TPB * D;
   const size_t n_tile = (size_t)n_sel * p.ntiles * D;
   const size_t n_tmp = (nsec > 0 && zerophase) ? (size_t)n_sel * n : 0;
-  QMB_TRY(ctx->pp_scratch.ensure(n_stats + n_mpow + n_chunk + 2 * n_tile + n_tmp + 8));
+  // single-pass form (default): no per-chunk state arrays, but tile descriptors + the response table
+  const bool fused = nsec > 0 && !getenv("QMB_PP_LEGACY");
+  const size_t n_resp = (size_t)D * PP_L;
+  const size_t n_desc = fused ? (size_t)n_sel * p.ntiles * 2 * D : 0;
+  const size_t n_flags = fused ? ((size_t)n_sel * p.ntiles + 1 + 1) / 2 + 1 : 0;  // ints, counted in doubles
+  QMB_TRY(ctx->pp_scratch.ensure(n_stats + n_mpow + n_resp + (fused ? n_desc + n_flags : n_chunk + 2 * n_tile) + n_tmp + 8));
   double *base = ctx->pp_scratch.p;
   double *d_stats = base; base += n_stats;
   double *d_mpow = base; base += n_mpow;
-  p.chunk_state = base; base += n_chunk;
-  p.tile_state = base; base += n_tile;
-  p.tile_in = base; base += n_tile;
+  double *d_resp = base; base += n_resp;
+  FusedScratch fs = {};
+  if (fused) {
+    fs.desc = base; base += n_desc;
+    fs.ticket = (int *)base;
+    fs.flags = fs.ticket + 1;
+    base += n_flags;
+    fs.resp = d_resp;
+  } else {
+    p.chunk_state = base; base += n_chunk;
+    p.tile_state = base; base += n_tile;
+    p.tile_in = base; base += n_tile;
+  }
   double *d_tmp = base;
   p.stats = d_stats;
   p.mpow = d_mpow;
@@ -466,8 +690,11 @@ int qmb_preprocess_device(qmb_ctx *ctx, const double *d_x, int64_t x_stride, con
           c[i * D + j] = acc;
         }
     }
+    std::vector<double> R;
+    zero_input_response(p.coef, nsec, PP_L, R);
+    pw.insert(pw.end(), R.begin(), R.end());  // d_resp follows d_mpow
     // pageable source: the copy is staged before the call returns
-    QMB_CUDA(cudaMemcpyAsync(d_mpow, pw.data(), n_mpow * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    QMB_CUDA(cudaMemcpyAsync(d_mpow, pw.data(), (n_mpow + n_resp) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     QMB_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   if (kernel_ms) QMB_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -489,13 +716,13 @@ int qmb_preprocess_device(qmb_ctx *ctx, const double *d_x, int64_t x_stride, con
     QMB_CUDA(cudaGetLastError());
   } else if (!zerophase) {
     p.y = d_out; p.y_stride = out_stride; p.chan_out0 = out_chan0; p.decimate = decimate;
-    QMB_TRY(run_pass_n(ctx, nsec, p, false));
+    QMB_TRY(fused ? run_pass_fused_n(ctx, nsec, p, fs, false) : run_pass_n(ctx, nsec, p, false));
   } else {
     p.y = d_tmp; p.y_stride = n; p.chan_out0 = 0; p.decimate = 1;
-    QMB_TRY(run_pass_n(ctx, nsec, p, false));
+    QMB_TRY(fused ? run_pass_fused_n(ctx, nsec, p, fs, false) : run_pass_n(ctx, nsec, p, false));
     p.x = d_tmp; p.x_stride = n; p.chan_in = nullptr; p.apply_pre = 0;
     p.y = d_out; p.y_stride = out_stride; p.chan_out0 = out_chan0; p.decimate = decimate;
-    QMB_TRY(run_pass_n(ctx, nsec, p, true));
+    QMB_TRY(fused ? run_pass_fused_n(ctx, nsec, p, fs, true) : run_pass_n(ctx, nsec, p, true));
   }
   if (kernel_ms) {
     QMB_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
