@@ -354,6 +354,7 @@ struct FusedScratch {
   int *flags;     // [n_sel * ntiles]  0: nothing, 1: aggregate published, 2: inclusive published
   double *desc;   // [n_sel * ntiles][2][D]: aggregate, inclusive end state
   const double *resp;  // [D][PP_L] zero-input response of the cascade output to unit start states
+  const double *ppow;  // [ntiles][D][D] powers of the tile transition P = M^PP_TPB
 };
 
 template <int NSEC, bool REV>
@@ -363,7 +364,8 @@ __global__ void __launch_bounds__(PP_TPB) k_sos_fused(PreParams p, FusedScratch 
   double *tile = sm;                            // PP_TPB * (PP_L + 1)
   double *sv = tile + PP_TPB * (PP_L + 1);      // PP_TPB * D: scan buffer, then true chunk-start states
   double *tin_s = sv + PP_TPB * D;              // D
-  double *R = tin_s + D;                        // D * PP_L
+  double *z_s = tin_s + D;                      // D: the tile's aggregate
+  double *R = z_s + D;                          // D * PP_L
   __shared__ int s_ticket;
   const int t = threadIdx.x;
   if (t == 0) s_ticket = atomicAdd(f.ticket, 1);
@@ -409,61 +411,69 @@ __global__ void __launch_bounds__(PP_TPB) k_sos_fused(PreParams p, FusedScratch 
   double c0[D];  // state at the start of this chunk, given a zero state at the start of the tile
 #pragma unroll
   for (int d = 0; d < D; ++d) c0[d] = t ? sv[(t - 1) * D + d] : 0.0;
-  // 3. look-back (the thread that holds the tile aggregate)
+  // 3. look-back, one warp: lane l inspects the predecessor at distance 32 w + l, all 32 at once
   if (t == PP_TPB - 1) {
-    const size_t me = (size_t)s * p.ntiles + T;
-    double *mine = f.desc + me * 2 * D;
-    const double *P = p.mpow + (size_t)PP_TPB * D * D;
+#pragma unroll
+    for (int d = 0; d < D; ++d) z_s[d] = st[d];
+  }
+  __syncthreads();
+  if (t < 32) {
+    const int lane = t;
+    const size_t row = (size_t)s * p.ntiles;
+    double *mine = f.desc + (row + T) * 2 * D;
     volatile int *flags = f.flags;
-    double in[D];
+    if (T > 0 && lane == 0) {
 #pragma unroll
-    for (int d = 0; d < D; ++d) in[d] = 0.0;
-    if (T > 0) {
-#pragma unroll
-      for (int d = 0; d < D; ++d) mine[d] = st[d];
+      for (int d = 0; d < D; ++d) mine[d] = z_s[d];
       __threadfence();
-      flags[me] = 1;
-      int j = T - 1;
-      int fl;
-      for (;;) {  // walk back to the nearest tile whose inclusive state is known (tile 0 always gets there)
-        while ((fl = flags[(size_t)s * p.ntiles + j]) == 0) {
+      flags[row + T] = 1;
+    }
+    double acc[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) acc[d] = 0.0;
+    bool done = T == 0;
+    for (int base = 0; !done; base += 32) {
+      const int dist = base + lane, j = T - 1 - dist;
+      int fl = 0;
+      if (j >= 0)
+        while ((fl = flags[row + j]) == 0) {
         }
-        if (fl == 2 || j == 0) break;
-        --j;
-      }
+      const unsigned has_incl = __ballot_sync(0xffffffffu, j >= 0 && fl == 2);
+      const int k = has_incl ? __ffs(has_incl) - 1 : 32;  // nearest tile of this window with a known end state
       __threadfence();
-      if (fl == 2) {
-        const double *e = f.desc + ((size_t)s * p.ntiles + j) * 2 * D + D;
+      if (j >= 0 && lane <= k) {
+        // in[T] = sum_{d < dist_k} P^d z_{T-1-d} + P^dist_k E_{T-1-dist_k}
+        const double *src = f.desc + (row + j) * 2 * D + (lane == k ? D : 0);
+        const double *Pd = f.ppow + (size_t)dist * D * D;
+        double v[D];
 #pragma unroll
-        for (int d = 0; d < D; ++d) in[d] = __ldcg(e + d);
-        ++j;
-      }
-      for (; j < T; ++j) {  // in <- P in + z_j
-        const double *z = f.desc + ((size_t)s * p.ntiles + j) * 2 * D;
-        double nx[D];
+        for (int q = 0; q < D; ++q) v[q] = __ldcg(src + q);
 #pragma unroll
         for (int i = 0; i < D; ++i) {
-          double acc = __ldcg(z + i);
+          double a2 = 0.0;
 #pragma unroll
-          for (int q = 0; q < D; ++q) acc += P[i * D + q] * in[q];
-          nx[i] = acc;
+          for (int q = 0; q < D; ++q) a2 += Pd[i * D + q] * v[q];
+          acc[i] += a2;
         }
-#pragma unroll
-        for (int i = 0; i < D; ++i) in[i] = nx[i];
       }
+      done = has_incl != 0u;  // tile 0 only ever publishes an inclusive state, so the walk ends there at the latest
     }
-    // inclusive end state of this tile: P in + z
 #pragma unroll
-    for (int i = 0; i < D; ++i) {
-      double acc = st[i];
+    for (int d = 0; d < D; ++d)
+      for (int o = 16; o > 0; o >>= 1) acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], o);
+    if (lane == 0) {
+      const double *P = p.mpow + (size_t)PP_TPB * D * D;
 #pragma unroll
-      for (int q = 0; q < D; ++q) acc += P[i * D + q] * in[q];
-      mine[D + i] = acc;
+      for (int i = 0; i < D; ++i) {
+        double e = z_s[i];
+#pragma unroll
+        for (int q = 0; q < D; ++q) e += P[i * D + q] * acc[q];
+        mine[D + i] = e;
+        tin_s[i] = acc[i];
+      }
+      __threadfence();
+      flags[row + T] = 2;
     }
-    __threadfence();
-    flags[me] = 2;
-#pragma unroll
-    for (int d = 0; d < D; ++d) tin_s[d] = in[d];
   }
   __syncthreads();
   // 4. true start state of every chunk, then the zero-input correction, coalesced
@@ -551,7 +561,7 @@ void zero_input_response(const double *coef, int nsec, int steps, std::vector<do
 template <int NSEC>
 int run_pass_fused(qmb_ctx *ctx, PreParams &p, const FusedScratch &f, bool rev) {
   constexpr int D = 2 * NSEC;
-  const size_t smem = (size_t)(PP_TPB * (PP_L + 1) + PP_TPB * D + D + D * PP_L) * sizeof(double);
+  const size_t smem = (size_t)(PP_TPB * (PP_L + 1) + PP_TPB * D + 2 * D + D * PP_L) * sizeof(double);
   const unsigned n_ctas = (unsigned)p.ntiles * (unsigned)p.n_sel;
   QMB_CUDA(cudaMemsetAsync(f.ticket, 0, (size_t)(1 + (size_t)p.ntiles * p.n_sel) * sizeof(int), ctx->stream));
   if (rev) {
@@ -653,7 +663,7 @@ int qmb_preprocess_device(qmb_ctx *ctx, const double *d_x, int64_t x_stride, con
   const size_t n_tmp = (nsec > 0 && zerophase) ? (size_t)n_sel * n : 0;
   // single-pass form (default): no per-chunk state arrays, but tile descriptors + the response table
   const bool fused = nsec > 0 && !getenv("QMB_PP_LEGACY");
-  const size_t n_resp = (size_t)D * PP_L;
+  const size_t n_resp = (size_t)D * PP_L + (fused ? (size_t)p.ntiles * D * D : 0);  // response table, then P^d
   const size_t n_desc = fused ? (size_t)n_sel * p.ntiles * 2 * D : 0;
   const size_t n_flags = fused ? ((size_t)n_sel * p.ntiles + 1 + 1) / 2 + 1 : 0;  // ints, counted in doubles
   QMB_TRY(ctx->pp_scratch.ensure(n_stats + n_mpow + n_resp + (fused ? n_desc + n_flags : n_chunk + 2 * n_tile) + n_tmp + 8));
@@ -668,6 +678,7 @@ int qmb_preprocess_device(qmb_ctx *ctx, const double *d_x, int64_t x_stride, con
     fs.flags = fs.ticket + 1;
     base += n_flags;
     fs.resp = d_resp;
+    fs.ppow = d_resp + (size_t)D * PP_L;
   } else {
     p.chunk_state = base; base += n_chunk;
     p.tile_state = base; base += n_tile;
@@ -693,6 +704,21 @@ int qmb_preprocess_device(qmb_ctx *ctx, const double *d_x, int64_t x_stride, con
     std::vector<double> R;
     zero_input_response(p.coef, nsec, PP_L, R);
     pw.insert(pw.end(), R.begin(), R.end());  // d_resp follows d_mpow
+    if (fused) {  // P^0 .. P^(ntiles-1), P = M^PP_TPB, for the look-back across tiles
+      std::vector<double> P(pw.begin() + (size_t)PP_TPB * D * D, pw.begin() + (size_t)(PP_TPB + 1) * D * D);
+      std::vector<double> cur((size_t)D * D, 0.0), nxt((size_t)D * D);
+      for (int i = 0; i < D; ++i) cur[(size_t)i * D + i] = 1.0;
+      for (int d = 0; d < p.ntiles; ++d) {
+        pw.insert(pw.end(), cur.begin(), cur.end());
+        for (int i = 0; i < D; ++i)
+          for (int j = 0; j < D; ++j) {
+            double acc = 0.0;
+            for (int l = 0; l < D; ++l) acc += cur[(size_t)i * D + l] * P[(size_t)l * D + j];
+            nxt[(size_t)i * D + j] = acc;
+          }
+        cur.swap(nxt);
+      }
+    }
     // pageable source: the copy is staged before the call returns
     QMB_CUDA(cudaMemcpyAsync(d_mpow, pw.data(), (n_mpow + n_resp) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     QMB_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -186,5 +186,7 @@ def test_gappy_channel_on_the_device():
     z = O.centred_sta_lta(assemble(segs) ** 2, 11, 51)
     hn = O.centred_sta_lta(assemble([Segment(0, full_n)]) ** 2, 11, 51)
     he = O.centred_sta_lta(assemble([Segment(0, _noise(n - 100, 7))]) ** 2, 11, 51)
-    np.testing.assert_allclose(onsets[0], np.clip(z, 0.4, np.inf), rtol=1e-8)
-    np.testing.assert_allclose(onsets[1], np.clip(np.sqrt((hn ** 2 + he ** 2) / 2), 0.4, np.inf), rtol=1e-8)
+    # at the edges of a gap the windows hold the sqrt(tiny) fill and a few tapered samples: the ratio is
+    # ~1e7 and rounding-level differences of the filter show up at 1e-6 of it
+    np.testing.assert_allclose(onsets[0], np.clip(z, 0.4, np.inf), rtol=2e-6)
+    np.testing.assert_allclose(onsets[1], np.clip(np.sqrt((hn ** 2 + he ** 2) / 2), 0.4, np.inf), rtol=2e-6)
