@@ -187,6 +187,11 @@ typedef struct qmb_ttgrids *qmb_ttgrids_t;
 int qmb_ttgrids_upload(qmb_ctx_t ctx, const double *grids, int32_t n_grids, int32_t nx, int32_t ny,
                        int32_t nz, qmb_ttgrids_t *out);
 int qmb_ttgrids_free(qmb_ttgrids_t grids);
+/* LUT.decimate (quakemigrate/lut/lut.py:102-140) on resident grids: every df-th node per axis,
+ * centred; returns new grids (the caller rescales node_spacing, lut.py:128).  qmb_ttgrids_shape
+ * writes (n_grids, nx, ny, nz). */
+int qmb_ttgrids_decimate(qmb_ctx_t ctx, qmb_ttgrids_t grids, const int32_t *df /* 3 */, qmb_ttgrids_t *out);
+int qmb_ttgrids_shape(qmb_ttgrids_t grids, int32_t *shape4);
 int qmb_lut_serve(qmb_ctx_t ctx, qmb_ttgrids_t grids, const int32_t *rows, int32_t n_rows,
                   double sampling_rate, int32_t x0, int32_t x1, qmb_lut_t *out);
 typedef struct {
@@ -244,6 +249,9 @@ int qmb_waveforms_filter(qmb_ctx_t ctx, qmb_waveforms_t in, const int32_t *chann
                          const double *sos, int32_t n_sections, int32_t detrend, double taper_fraction,
                          int32_t zerophase, int32_t decimate, qmb_waveforms_t out, int32_t out_chan0,
                          float *kernel_ms);
+/* util.upsample's fence-post linear interpolation (quakemigrate/util.py:544-551) of every trace of a
+ * block: (n - 1) * upfactor + 1 samples per trace, bit-identical to the numpy expression. */
+int qmb_waveforms_upsample(qmb_ctx_t ctx, qmb_waveforms_t in, int32_t upfactor, qmb_waveforms_t *out);
 int qmb_onsets_from_device_waveforms(qmb_ctx_t ctx, qmb_waveforms_t w, int32_t n_rows,
                                      const int32_t *row_ptr, const int32_t *row_chan,
                                      const int32_t *nsta, const int32_t *nlta, int32_t position,

@@ -104,6 +104,8 @@ SIGNATURES = {
     "qmb_ttgrids_upload": (ctypes.c_int, [c_void_p, c_dPt, c_int32, c_int32, c_int32, c_int32,
                                           ctypes.POINTER(c_void_p)]),
     "qmb_ttgrids_free": (ctypes.c_int, [c_void_p]),
+    "qmb_ttgrids_decimate": (ctypes.c_int, [c_void_p, c_void_p, c_i32Pt, ctypes.POINTER(c_void_p)]),
+    "qmb_ttgrids_shape": (ctypes.c_int, [c_void_p, c_i32Pt]),
     "qmb_lut_serve": (ctypes.c_int, [c_void_p, c_void_p, c_i32Pt, c_int32, c_double, c_int32, c_int32,
                                      ctypes.POINTER(c_void_p)]),
     "qmb_lut_info": (ctypes.c_int, [c_void_p, ctypes.POINTER(LutInfo)]),
@@ -119,6 +121,7 @@ SIGNATURES = {
     "qmb_waveforms_filter": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int32,
                                             c_int32, c_double, c_int32, c_int32, c_void_p, c_int32,
                                             c_void_p]),
+    "qmb_waveforms_upsample": (ctypes.c_int, [c_void_p, c_void_p, c_int32, ctypes.POINTER(c_void_p)]),
     "qmb_onsets_from_device_waveforms": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_i32Pt, c_i32Pt,
                                                         c_i32Pt, c_i32Pt, c_int32, c_int32, c_double,
                                                         c_void_p, ctypes.POINTER(c_void_p)]),

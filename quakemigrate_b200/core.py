@@ -166,6 +166,15 @@ class DeviceGrids:
     def __init__(self, engine, handle, shape):
         self.engine, self._h, self.shape = engine, handle, tuple(shape)
 
+    def decimate(self, df) -> "DeviceGrids":
+        """``LUT.decimate`` (lut.py:102-140) on the device: every ``df``-th node per axis, centred."""
+        d = np.ascontiguousarray(np.broadcast_to(np.asarray(df, dtype=np.int32), (3,)))
+        h = ctypes.c_void_p()
+        _lib.check(_lib.load().qmb_ttgrids_decimate(self.engine._h, self._h, d, ctypes.byref(h)))
+        shape = np.zeros(4, dtype=np.int32)
+        _lib.check(_lib.load().qmb_ttgrids_shape(h, shape))
+        return DeviceGrids(self.engine, h, tuple(int(v) for v in shape))
+
     def free(self):
         if self._h:
             _lib.load().qmb_ttgrids_free(self._h)
@@ -270,6 +279,12 @@ class DeviceWaveforms:
     @property
     def shape(self):
         return (self.n_channels, self.n)
+
+    def upsample(self, upfactor: int) -> "DeviceWaveforms":
+        """The interpolation of ``util.upsample`` (util.py:544-551) on the device: a new block."""
+        h = ctypes.c_void_p()
+        _lib.check(_lib.load().qmb_waveforms_upsample(self.engine._h, self._h, int(upfactor), ctypes.byref(h)))
+        return DeviceWaveforms(self.engine, h, self.n_channels, (self.n - 1) * int(upfactor) + 1)
 
     def fetch(self, chan0: int = 0, n_chan: int | None = None) -> np.ndarray:
         n_chan = self.n_channels - chan0 if n_chan is None else n_chan

@@ -360,3 +360,61 @@ int qmb_lut_build(qmb_ctx *ctx, qmb_lut *L, const int32_t *d_raw, const QmbServe
            "travel-time range inside one node tile (%d samples) is too wide for the shared-memory pipeline",
            L->max_span);
 }
+
+// ---------------------------------------------------------------------------------------------
+// LUT.decimate on the device (quakemigrate/lut/lut.py:102-140): keep every df-th node per axis,
+// starting c1 nodes in so that the kept nodes are centred; one strided gather per grid.
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) k_grid_decimate(const double *in, double *out, int nx, int ny, int nz, int mx,
+                                                       int my, int mz, int dx, int dy, int dz, int cx, int cy, int cz) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per = (long long)mx * my * mz;
+  if (m >= per) return;
+  const int g = blockIdx.y;
+  const int k = (int)(m % mz), j = (int)((m / mz) % my), i = (int)(m / ((long long)mz * my));
+  const long long src = ((long long)(cx + i * dx) * ny + (cy + j * dy)) * nz + (cz + k * dz);
+  out[(size_t)g * per + m] = in[(size_t)g * nx * ny * nz + src];
+}
+}  // namespace
+
+extern "C" int qmb_ttgrids_decimate(qmb_ctx_t ctx, qmb_ttgrids_t G, const int32_t *df, qmb_ttgrids_t *out) {
+  if (!ctx || !G || !df || !out) QMB_FAIL(QMB_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (G->ctx != ctx) QMB_FAIL(QMB_ERR_ARG, "grids belong to a different context");
+  if (df[0] < 1 || df[1] < 1 || df[2] < 1) QMB_FAIL(QMB_ERR_ARG, "decimation factors must be >= 1");
+  QMB_CUDA(cudaSetDevice(ctx->device));
+  const int n[3] = {G->nx, G->ny, G->nz};
+  int m[3], c[3];
+  for (int a = 0; a < 3; ++a) {
+    m[a] = 1 + (n[a] - 1) / df[a];                         // lut.py:123
+    c[a] = (n[a] - df[a] * (m[a] - 1) - 1) / 2;            // lut.py:124
+  }
+  qmb_ttgrids *D = new qmb_ttgrids();
+  D->ctx = ctx; D->device = ctx->device; D->n_grids = G->n_grids; D->nx = m[0]; D->ny = m[1]; D->nz = m[2];
+  const long long per = (long long)m[0] * m[1] * m[2];
+  int rc = D->tt.ensure((size_t)G->n_grids * per);
+  if (rc != QMB_OK) {
+    delete D;
+    return rc;
+  }
+  dim3 grid((unsigned)((per + 255) / 256), (unsigned)G->n_grids);
+  k_grid_decimate<<<grid, 256, 0, ctx->stream>>>(G->tt.p, D->tt.p, n[0], n[1], n[2], m[0], m[1], m[2], df[0], df[1], df[2],
+                                                 c[0], c[1], c[2]);
+  ctx->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    D->tt.release();
+    delete D;
+    QMB_FAIL(QMB_ERR_CUDA, "qmb_ttgrids_decimate: %s", cudaGetErrorString(e));
+  }
+  *out = D;
+  return QMB_OK;
+}
+
+extern "C" int qmb_ttgrids_shape(qmb_ttgrids_t G, int32_t *shape4) {
+  if (!G || !shape4) QMB_FAIL(QMB_ERR_ARG, "null argument");
+  shape4[0] = G->n_grids; shape4[1] = G->nx; shape4[2] = G->ny; shape4[3] = G->nz;
+  return QMB_OK;
+}

@@ -53,6 +53,7 @@ struct PreParams {
   const double *stats;    // [n_sel][2]  mean, slope about the trace centre
   double tbar;            // (n - 1) / 2
   long long wlen;         // taper half-length in samples (0: none)
+  const double *taper;    // [2][wlen]: weights of the first / last wlen samples (k_taper_table)
   int decimate;           // keep samples with index % decimate == 0 (final pass only)
   double coef[PP_MAX_SEC * 5];  // per section: b0 b1 b2 a1 a2 (a0 == 1)
   const double *mpow;     // [(PP_TPB + 1)][D][D]: M^k, M = zero-input state transition of one chunk
@@ -86,11 +87,23 @@ __device__ __noinline__ double taper_weight(long long i, long long n, long long 
   return 1.0;
 }
 
+// The taper weights of a call, once: the tiles at either end of a trace would otherwise spend longer
+// in cos() than the others spend filtering (and, in the single-pass form, keep their successors waiting).
+__global__ void __launch_bounds__(256) k_taper_table(double *tw, long long n, long long wlen) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= wlen) return;
+  tw[k] = taper_weight(k, n, wlen);
+  tw[wlen + k] = taper_weight(n - wlen + k, n, wlen);
+}
+
 // detrend("linear") + detrend("constant") + cosine taper of sample i (element-wise kernels)
 __device__ __forceinline__ double pre_sample(const PreParams &p, double v, long long i, double mean,
                                              double slope) {
   v -= mean + slope * ((double)i - p.tbar);
-  if (p.wlen > 0 && (i < p.wlen || i >= p.n - p.wlen)) v *= taper_weight(i, p.n, p.wlen);
+  if (p.wlen > 0) {
+    if (i < p.wlen) v *= p.taper[i];
+    else if (i >= p.n - p.wlen) v *= p.taper[p.wlen + (i - (p.n - p.wlen))];
+  }
   return v;
 }
 
@@ -136,7 +149,8 @@ __device__ __forceinline__ void load_tile(const PreParams &p, double *tile, int 
         const long long q = q0 + (long long)j * PP_TPB;
         if (q >= p.n) break;
         const long long i = REV ? p.n - 1 - q : q;
-        if (i < p.wlen || i >= p.n - p.wlen) dst[j * STEP] *= taper_weight(i, p.n, p.wlen);
+        if (i < p.wlen) dst[j * STEP] *= p.taper[i];
+        else if (i >= p.n - p.wlen) dst[j * STEP] *= p.taper[p.wlen + (i - (p.n - p.wlen))];
       }
     }
   }
@@ -666,9 +680,12 @@ int qmb_preprocess_device(qmb_ctx *ctx, const double *d_x, int64_t x_stride, con
   const size_t n_resp = (size_t)D * PP_L + (fused ? (size_t)p.ntiles * D * D : 0);  // response table, then P^d
   const size_t n_desc = fused ? (size_t)n_sel * p.ntiles * 2 * D : 0;
   const size_t n_flags = fused ? ((size_t)n_sel * p.ntiles + 1 + 1) / 2 + 1 : 0;  // ints, counted in doubles
-  QMB_TRY(ctx->pp_scratch.ensure(n_stats + n_mpow + n_resp + (fused ? n_desc + n_flags : n_chunk + 2 * n_tile) + n_tmp + 8));
+  const size_t n_taper = (size_t)2 * p.wlen;
+  QMB_TRY(ctx->pp_scratch.ensure(n_stats + n_taper + n_mpow + n_resp + (fused ? n_desc + n_flags : n_chunk + 2 * n_tile) + n_tmp + 8));
   double *base = ctx->pp_scratch.p;
   double *d_stats = base; base += n_stats;
+  double *d_taper = base; base += n_taper;
+  p.taper = d_taper;
   double *d_mpow = base; base += n_mpow;
   double *d_resp = base; base += n_resp;
   FusedScratch fs = {};
@@ -733,6 +750,11 @@ int qmb_preprocess_device(qmb_ctx *ctx, const double *d_x, int64_t x_stride, con
   k_pre_stats<<<n_sel, 32, 0, ctx->stream>>>(p, d_partial, d_stats, detrend ? 1 : 0);
   ctx->launches++;
   QMB_CUDA(cudaGetLastError());
+  if (p.wlen > 0) {
+    k_taper_table<<<(unsigned)((p.wlen + 255) / 256), 256, 0, ctx->stream>>>(d_taper, n, p.wlen);
+    ctx->launches++;
+    QMB_CUDA(cudaGetLastError());
+  }
   p.apply_pre = 1;
   if (nsec == 0) {
     p.y = d_out; p.y_stride = out_stride; p.chan_out0 = out_chan0; p.decimate = decimate;
@@ -843,6 +865,41 @@ extern "C" int qmb_waveforms_filter(qmb_ctx_t ctx, qmb_waveforms_t in, const int
   }
   return qmb_preprocess_device(ctx, in->data.p, in->n, d_sel, n_sel, in->n, sos, n_sections, detrend,
                                taper_fraction, zerophase, decimate, out->data.p, out->n, out_chan0, kernel_ms);
+}
+
+// util.upsample's interpolation (quakemigrate/util.py:544-551): fence-post linear interpolation,
+// out[i * up + r] = r/up * x[i+1] + (up-r)/up * x[i]; products and sum rounded separately like numpy
+namespace {
+__global__ void __launch_bounds__(256) k_upsample(const double *x, long long n, int up, double *y, long long m) {
+  const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= m) return;
+  const double *xs = x + (size_t)blockIdx.y * n;
+  const long long i = o / up;
+  const int r = (int)(o % up);
+  double v = xs[i];
+  if (r) v = __dadd_rn(__dmul_rn((double)r / (double)up, xs[i + 1]), __dmul_rn((double)(up - r) / (double)up, v));
+  y[(size_t)blockIdx.y * m + o] = v;
+}
+}  // namespace
+
+extern "C" int qmb_waveforms_upsample(qmb_ctx_t ctx, qmb_waveforms_t in, int32_t upfactor, qmb_waveforms_t *out) {
+  if (!ctx || !in || !out) QMB_FAIL(QMB_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (in->ctx != ctx) QMB_FAIL(QMB_ERR_ARG, "handles belong to a different context");
+  if (upfactor < 1) QMB_FAIL(QMB_ERR_ARG, "upfactor must be >= 1");
+  QMB_CUDA(cudaSetDevice(ctx->device));
+  const int64_t m = (in->n - 1) * upfactor + 1;
+  QMB_TRY(qmb_waveforms_alloc(ctx, in->C, m, out));
+  dim3 grid((unsigned)((m + 255) / 256), (unsigned)in->C);
+  k_upsample<<<grid, 256, 0, ctx->stream>>>(in->data.p, in->n, upfactor, (*out)->data.p, m);
+  ctx->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    qmb_waveforms_free(*out);
+    *out = nullptr;
+    QMB_FAIL(QMB_ERR_CUDA, "qmb_waveforms_upsample: %s", cudaGetErrorString(e));
+  }
+  return QMB_OK;
 }
 
 // one call, host in / host out

@@ -141,6 +141,14 @@ class LUT(Grid3D):
                           for (st, ph) in index], axis=0)
         return engine.upload_traveltime_grids(stack), index
 
+    def decimated_grid(self, df) -> "Grid3D":
+        """The grid of ``self.decimate(df)`` without touching the tables (lut.py:123-128): for use
+        with ``DeviceGrids.decimate(df)``, which does the gather on the device."""
+        df = np.broadcast_to(np.asarray(df, dtype=int), (3,))
+        g = Grid3D(1 + (self.node_count - 1) // df, self.node_spacing * df, self.ll_corner, self.grid2coord)
+        g.unit_conversion_factor = self.unit_conversion_factor
+        return g
+
     @staticmethod
     def rows_for(availability, index):
         """Grid index per served row for an availability dict (lut.py:527-537 ordering)."""

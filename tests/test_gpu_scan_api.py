@@ -166,3 +166,40 @@ def test_onset_timespan_nulls_taper_windows():
     want[:, -(nsta + taper):] = 1.0
     assert np.array_equal(nulled, want)
     eng.close()
+
+
+def test_decimate_and_upsample_on_the_device():
+    """LUT.decimate (lut.py:102-140) and util.upsample's interpolation (util.py:544-551) on resident
+    data: bit-identical to the host forms."""
+    from quakemigrate_b200.core import Engine
+    from quakemigrate_b200.lut import LUT
+    from quakemigrate_b200.preprocess import upsample
+    rng = np.random.default_rng(4)
+    shape = (17, 14, 11)
+    tts = {f"S{k}": {"P": rng.random(shape), "S": rng.random(shape) * 1.7} for k in range(3)}
+    lut = LUT(tts, shape, [0.5, 0.5, 0.5], [0.0, 0.0, -1.0])
+    with Engine(0) as eng:
+        grids, index = lut.to_device(eng)
+        for df in ([2, 3, 4], [1, 1, 1], [5, 5, 5]):
+            dec = lut.decimate(df)
+            dgr = grids.decimate(df)
+            assert dgr.shape == (6,) + tuple(dec.node_count)
+            assert list(lut.decimated_grid(df).node_count) == list(dec.node_count)
+            avail = {f"{st}_{ph}": 1 for ph in ("P", "S") for st in tts}
+            rows = LUT.rows_for(avail, index)
+            dl = eng.serve_lut(dgr, rows, 100.0)
+            want = dec.serve_traveltimes(100.0, avail)
+            onsets = np.clip(rng.gamma(2.0, 0.6, size=(6, 700)), 0.4, None)
+            ref = eng.upload_lut(want)
+            a = eng.detect(dl, onsets, 10, 200, 6)
+            b = eng.detect(ref, onsets, 10, 200, 6)
+            assert all(np.array_equal(x, y) for x, y in zip(a, b))
+            dgr.free()
+        grids.free()
+        wf = rng.standard_normal((5, 333))
+        dev = eng.upload_waveforms(wf)
+        for up in (1, 2, 5):
+            got = dev.upsample(up)
+            want = np.stack([upsample(row, up) for row in wf])
+            assert np.array_equal(got.fetch(), want)
+            got.free()

@@ -189,4 +189,11 @@ def test_gappy_channel_on_the_device():
     # at the edges of a gap the windows hold the sqrt(tiny) fill and a few tapered samples: the ratio is
     # ~1e7 and rounding-level differences of the filter show up at 1e-6 of it
     np.testing.assert_allclose(onsets[0], np.clip(z, 0.4, np.inf), rtol=2e-6)
-    np.testing.assert_allclose(onsets[1], np.clip(np.sqrt((hn ** 2 + he ** 2) / 2), 0.4, np.inf), rtol=2e-6)
+    # The E trace ends 100 samples early.  Once BOTH windows of a sample lie in the sqrt(tiny) fill the
+    # reference's sliding sums hold nothing but the rounding residue of the data that left them
+    # (onsetlib.c:98-107 adds and subtracts), i.e. noise; the device sums come out as exact zeros and
+    # the "lta <= 0 -> 1" rule applies.  Compare where at least the long window still sees data.
+    ok = np.arange(n) < n - 100 + 40
+    want_s = np.clip(np.sqrt((hn ** 2 + he ** 2) / 2), 0.4, np.inf)
+    np.testing.assert_allclose(onsets[1][ok], want_s[ok], rtol=2e-6)
+    assert np.isfinite(onsets[1]).all() and (onsets[1] >= 0.4).all()
