@@ -363,10 +363,23 @@ __global__ void __launch_bounds__(PP_TPB) k_sos_apply(PreParams p) {
 //      per sample, independent across samples, instead of a second serial pass of the cascade.
 // Rounding differs from scipy's sosfilt at the 1e-15 level of the trace's peak (the same level as
 // the three-kernel form, whose re-associated state propagation this shares).
+struct alignas(16) DescEntry {
+  double v;
+  unsigned long long valid;
+};
+__device__ __forceinline__ void desc_store(DescEntry *e, double v) {
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(e), "l"(__double_as_longlong(v)), "l"(1ull) : "memory");
+}
+__device__ __forceinline__ bool desc_load(const DescEntry *e, double &v) {
+  unsigned long long a, b;
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(e) : "memory");
+  v = __longlong_as_double((long long)a);
+  return b != 0ull;
+}
+
 struct FusedScratch {
-  int *ticket;    // [1] next tile to hand out, followed by
-  int *flags;     // [n_sel * ntiles]  0: nothing, 1: aggregate published, 2: inclusive published
-  double *desc;   // [n_sel * ntiles][2][D]: aggregate, inclusive end state
+  int *ticket;      // [1] next tile to hand out (4 ints reserved)
+  DescEntry *desc;  // [n_sel * ntiles][2][D]: aggregate, inclusive end state; zeroed before every pass
   const double *resp;  // [D][PP_L] zero-input response of the cascade output to unit start states
   const double *ppow;  // [ntiles][D][D] powers of the tile transition P = M^PP_TPB
 };
@@ -425,7 +438,9 @@ __global__ void __launch_bounds__(PP_TPB) k_sos_fused(PreParams p, FusedScratch 
   double c0[D];  // state at the start of this chunk, given a zero state at the start of the tile
 #pragma unroll
   for (int d = 0; d < D; ++d) c0[d] = t ? sv[(t - 1) * D + d] : 0.0;
-  // 3. look-back, one warp: lane l inspects the predecessor at distance 32 w + l, all 32 at once
+  // 3. look-back, one warp: lane l inspects the predecessor at distance 32 w + l, all 32 at once.
+  // A descriptor entry is 16 bytes, {value, valid}, written and read with ONE vector access, so a
+  // reader sees either nothing or the value: no flags array, no memory fences.
   if (t == PP_TPB - 1) {
 #pragma unroll
     for (int d = 0; d < D; ++d) z_s[d] = st[d];
@@ -434,34 +449,37 @@ __global__ void __launch_bounds__(PP_TPB) k_sos_fused(PreParams p, FusedScratch 
   if (t < 32) {
     const int lane = t;
     const size_t row = (size_t)s * p.ntiles;
-    double *mine = f.desc + (row + T) * 2 * D;
-    volatile int *flags = f.flags;
-    if (T > 0 && lane == 0) {
-#pragma unroll
-      for (int d = 0; d < D; ++d) mine[d] = z_s[d];
-      __threadfence();
-      flags[row + T] = 1;
-    }
+    DescEntry *mine = f.desc + (row + T) * 2 * D;  // [0, D): aggregate, [D, 2 D): inclusive end state
+    if (T > 0 && lane < D) desc_store(mine + lane, z_s[lane]);
     double acc[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) acc[d] = 0.0;
     bool done = T == 0;
     for (int base = 0; !done; base += 32) {
       const int dist = base + lane, j = T - 1 - dist;
-      int fl = 0;
-      if (j >= 0)
-        while ((fl = flags[row + j]) == 0) {
+      double v[D];
+      bool incl = false;
+      if (j >= 0) {
+        const DescEntry *e = f.desc + (row + j) * 2 * D;
+        for (;;) {  // the inclusive state if it is there, else the aggregate, else wait
+          bool ok = true;
+#pragma unroll
+          for (int q = 0; q < D; ++q) ok &= desc_load(e + D + q, v[q]);
+          if (ok) {
+            incl = true;
+            break;
+          }
+          ok = true;
+#pragma unroll
+          for (int q = 0; q < D; ++q) ok &= desc_load(e + q, v[q]);
+          if (ok) break;
         }
-      const unsigned has_incl = __ballot_sync(0xffffffffu, j >= 0 && fl == 2);
+      }
+      const unsigned has_incl = __ballot_sync(0xffffffffu, incl);
       const int k = has_incl ? __ffs(has_incl) - 1 : 32;  // nearest tile of this window with a known end state
-      __threadfence();
       if (j >= 0 && lane <= k) {
         // in[T] = sum_{d < dist_k} P^d z_{T-1-d} + P^dist_k E_{T-1-dist_k}
-        const double *src = f.desc + (row + j) * 2 * D + (lane == k ? D : 0);
         const double *Pd = f.ppow + (size_t)dist * D * D;
-        double v[D];
-#pragma unroll
-        for (int q = 0; q < D; ++q) v[q] = __ldcg(src + q);
 #pragma unroll
         for (int i = 0; i < D; ++i) {
           double a2 = 0.0;
@@ -475,18 +493,16 @@ __global__ void __launch_bounds__(PP_TPB) k_sos_fused(PreParams p, FusedScratch 
 #pragma unroll
     for (int d = 0; d < D; ++d)
       for (int o = 16; o > 0; o >>= 1) acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], o);
-    if (lane == 0) {
+    if (lane < D) {  // lane i: component i of the inclusive end state P in + z
       const double *P = p.mpow + (size_t)PP_TPB * D * D;
+      double e = z_s[lane];
 #pragma unroll
-      for (int i = 0; i < D; ++i) {
-        double e = z_s[i];
+      for (int q = 0; q < D; ++q) e += P[lane * D + q] * acc[q];
+      desc_store(mine + D + lane, e);
+    }
+    if (lane == 0) {
 #pragma unroll
-        for (int q = 0; q < D; ++q) e += P[i * D + q] * acc[q];
-        mine[D + i] = e;
-        tin_s[i] = acc[i];
-      }
-      __threadfence();
-      flags[row + T] = 2;
+      for (int i = 0; i < D; ++i) tin_s[i] = acc[i];
     }
   }
   __syncthreads();
@@ -577,7 +593,8 @@ int run_pass_fused(qmb_ctx *ctx, PreParams &p, const FusedScratch &f, bool rev) 
   constexpr int D = 2 * NSEC;
   const size_t smem = (size_t)(PP_TPB * (PP_L + 1) + PP_TPB * D + 2 * D + D * PP_L) * sizeof(double);
   const unsigned n_ctas = (unsigned)p.ntiles * (unsigned)p.n_sel;
-  QMB_CUDA(cudaMemsetAsync(f.ticket, 0, (size_t)(1 + (size_t)p.ntiles * p.n_sel) * sizeof(int), ctx->stream));
+  // ticket + descriptors are contiguous: one memset
+  QMB_CUDA(cudaMemsetAsync(f.ticket, 0, 16 + (size_t)p.ntiles * p.n_sel * 2 * D * sizeof(DescEntry), ctx->stream));
   if (rev) {
     QMB_CUDA(cudaFuncSetAttribute(k_sos_fused<NSEC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_sos_fused<NSEC, true><<<n_ctas, PP_TPB, smem, ctx->stream>>>(p, f);
@@ -678,10 +695,10 @@ int qmb_preprocess_device(qmb_ctx *ctx, const double *d_x, int64_t x_stride, con
   // single-pass form (default): no per-chunk state arrays, but tile descriptors + the response table
   const bool fused = nsec > 0 && !getenv("QMB_PP_LEGACY");
   const size_t n_resp = (size_t)D * PP_L + (fused ? (size_t)p.ntiles * D * D : 0);  // response table, then P^d
-  const size_t n_desc = fused ? (size_t)n_sel * p.ntiles * 2 * D : 0;
-  const size_t n_flags = fused ? ((size_t)n_sel * p.ntiles + 1 + 1) / 2 + 1 : 0;  // ints, counted in doubles
+  const size_t n_desc = fused ? (size_t)n_sel * p.ntiles * 2 * D * 2 : 0;  // 16-byte entries, counted in doubles
+  const size_t n_flags = fused ? 2 : 0;                                     // the ticket (16 bytes)
   const size_t n_taper = (size_t)2 * p.wlen;
-  QMB_TRY(ctx->pp_scratch.ensure(n_stats + n_taper + n_mpow + n_resp + (fused ? n_desc + n_flags : n_chunk + 2 * n_tile) + n_tmp + 8));
+  QMB_TRY(ctx->pp_scratch.ensure(n_stats + n_taper + n_mpow + n_resp + (fused ? n_desc + n_flags + 2 : n_chunk + 2 * n_tile) + n_tmp + 8));
   double *base = ctx->pp_scratch.p;
   double *d_stats = base; base += n_stats;
   double *d_taper = base; base += n_taper;
@@ -690,10 +707,9 @@ int qmb_preprocess_device(qmb_ctx *ctx, const double *d_x, int64_t x_stride, con
   double *d_resp = base; base += n_resp;
   FusedScratch fs = {};
   if (fused) {
-    fs.desc = base; base += n_desc;
-    fs.ticket = (int *)base;
-    fs.flags = fs.ticket + 1;
-    base += n_flags;
+    if (((uintptr_t)base & 15u) != 0) ++base;  // 16-byte alignment of the descriptor entries
+    fs.ticket = (int *)base; base += n_flags;
+    fs.desc = (DescEntry *)base; base += n_desc;
     fs.resp = d_resp;
     fs.ppow = d_resp + (size_t)D * PP_L;
   } else {
