@@ -52,7 +52,7 @@ def test_golden_pre_process(eng):
     _close(eng.preprocess(raw, None), GOLD["detrend_taper"], rtol=1e-11)
 
 
-@pytest.mark.parametrize("n", [3, 19, 20, 33, 40, 1000, 8191, 8192, 8193, 20000, 70001])
+@pytest.mark.parametrize("n", [3, 19, 20, 33, 40, 1000, 4095, 4096, 4097, 8191, 8192, 8193, 20000, 70001])
 def test_lengths_around_chunk_and_tile_edges(eng, n):
     rng = np.random.default_rng(n)
     x = _traces(rng, 3, n)
