@@ -113,7 +113,7 @@ def git_head() -> str:
         return "unknown"
 
 
-def ncu_traffic(workload: str, variant: int, operand_bytes: int):
+def ncu_traffic(workload: str, variant: int, operand_bits: int):
     """
     DRAM bytes per launch of k_scan from the committed `ncu --set full` capture of the SAME
     (workload, tiling variant, operand format): profiles/scan_ncu_summary.json holds one entry per
@@ -126,7 +126,7 @@ def ncu_traffic(workload: str, variant: int, operand_bytes: int):
         pj = json.loads(prof.read_text())
     except Exception:
         return None, None
-    key = f"{workload}:v{variant}:{'q16' if operand_bytes == 2 else 'fp32'}"
+    key = f"{workload}:v{variant}:" + ("fp32" if operand_bits >= 32 else f"q{operand_bits}")
     ent = (pj.get("entries") or {}).get(key)
     if not ent:
         return None, None
@@ -454,7 +454,7 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
     bpg = eng.last_scan_bytes_per_gather
     traffic, traffic_src = (None, None)
     if world == 1 and not args.samples:
-        traffic, traffic_src = ncu_traffic(base.name, info["variant"], bpg)
+        traffic, traffic_src = ncu_traffic(base.name, info["variant"], scan_info["operand_bits"])
     measured_pipe = eng.smem_pipe_peak()
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     ga = float(N_local) * T * S / (scan_mean * 1e-3)

@@ -855,11 +855,19 @@ __global__ void __launch_bounds__(256) k_finalize(MState g, const double *ex1, c
       two = true;
       const double other = exp(ex2[t] / avail);
       const long long oi = g.i2[tp];
-      if (oi != 0xFFFFFFFFLL && (other > best || (other == best && oi < idx))) {
-        best = other;
-        idx = oi;
+      double known = ex1[t];  // best EXACT stack among the two evaluated candidates
+      if (oi != 0xFFFFFFFFLL) {
+        known = fmax(known, ex2[t]);
+        if (other > best || (other == best && oi < idx)) {
+          best = other;
+          idx = oi;
+        }
       }
-      slow = a1 - a3 <= thr;
+      // Every other node (the third included) has a scan stack <= m3, hence an exact stack
+      // <= m3 + delta (thr = 2 delta).  Only if that could reach the best known exact stack does the
+      // sample need the all-node float64 re-scan -- roughly m1 - m3 < delta instead of < 2 delta.
+      // The margin keeps exp() of the two sides distinguishable in float64.
+      slow = !(known > (double)a3 + 0.5 * (double)thr + 1e-10 * fmax(1.0, fabs(known)));
     }
     slow_flag[t] = slow ? 1 : 0;
     r_max[t] = best;

@@ -1,0 +1,13 @@
+#!/bin/bash
+# Round 2, visit L: full GPU suite on the final code + the bench lines and launch lists for profiles/.
+set -x
+mkdir -p gpurun_out
+timeout 200 python __graft_entry__.py --smoke 2>&1 | tail -2
+timeout 1800 python -m pytest tests -q -m gpu 2>&1 > gpurun_out/r2l_gpu_tests_full.log; tail -6 gpurun_out/r2l_gpu_tests_full.log
+timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/r2l_bench_n1_cfg3.json 2> gpurun_out/r2l_bench_n1_cfg3.err; tail -c 300 gpurun_out/r2l_bench_n1_cfg3.json; tail -3 gpurun_out/r2l_bench_n1_cfg3.err
+timeout 300 python bench.py --workload cfg2 --steps 10 --warmup 3 > gpurun_out/r2l_bench_n1_cfg2.json 2> gpurun_out/r2l_bench_n1_cfg2.err; tail -c 300 gpurun_out/r2l_bench_n1_cfg2.json; tail -3 gpurun_out/r2l_bench_n1_cfg2.err
+timeout 300 python bench.py --workload cfg4 --steps 5 --warmup 2 > gpurun_out/r2l_bench_n1_cfg4_locate.json 2> gpurun_out/r2l_bench_n1_cfg4_locate.err; tail -c 300 gpurun_out/r2l_bench_n1_cfg4_locate.json; tail -3 gpurun_out/r2l_bench_n1_cfg4_locate.err
+timeout 300 python bench.py --impl reference --steps 5 --warmup 2 > gpurun_out/r2l_bench_reference_cfg3.json 2> gpurun_out/r2l_bench_reference_cfg3.err; tail -c 300 gpurun_out/r2l_bench_reference_cfg3.json
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2l_launches_cfg2.csv python bench.py --workload cfg2 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r2l_ncu_launches.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2l_launches_cfg4.csv python bench.py --workload cfg4 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/r2l_ncu_launches_cfg4.log 2>&1
+ls -la gpurun_out | grep r2l
