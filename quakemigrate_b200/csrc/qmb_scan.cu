@@ -933,7 +933,18 @@ __global__ void __launch_bounds__(1024) k_slow_compact(const unsigned char *flag
 // read from the device, batches of SLOW_BATCH samples are walked inside the kernel.
 constexpr int SLOW_BATCH = 8;
 constexpr int SLOW_CAP = 4096;  // queued samples handled per round (more: further rounds)
-__global__ void __launch_bounds__(128) k_slow(ExactParams e, const int *slow_list, int cap, double avail,
+// Node subsets that can hold the arg-max: the scan kept one running maximum per (node range r,
+// warp w) and sample -- the partial pm1[(r * W + w) * Tpad + t] -- and the exact arg-max node has a
+// scan stack >= m1 - thr (exact(n*) >= exact(i1) >= m1 - delta, scan(n*) >= exact(n*) - delta), so
+// only subsets whose partial maximum reaches m1 - thr need the float64 walk for that sample.
+struct SlowFilter {
+  const float *pm1;  // null: no filter (partials already overwritten)
+  const float *gm1;  // merged m1 (all ranks)
+  long long Tpad;
+  int R, W, NPW, shift;
+  float thr;
+};
+__global__ void __launch_bounds__(128) k_slow(ExactParams e, SlowFilter f, const int *slow_list, int cap, double avail,
                                               const uint32_t *nodeidx, int n_tiles, double *part_val,
                                               unsigned long long *part_idx) {
   const int n_slow = slow_list[0];
@@ -953,6 +964,18 @@ __global__ void __launch_bounds__(128) k_slow(ExactParams e, const int *slow_lis
       if (j >= n_tiles || (int)threadIdx.x >= tiles_per_pass * e.NB) continue;
       const uint32_t gi = nodeidx[(size_t)j * e.NB + q];
       if (gi == 0xFFFFFFFFu) continue;
+      unsigned hot = (1u << nb) - 1u;
+      if (f.pm1) {
+        // range of tile j: the r with r * n_tiles / R <= j < (r + 1) * n_tiles / R (k_scan's split)
+        int r = (int)((((long long)j + 1) * f.R - 1) / n_tiles);
+        while (r > 0 && (long long)r * n_tiles / f.R > j) --r;
+        while (r + 1 < f.R && (long long)(r + 1) * n_tiles / f.R <= j) ++r;
+        const float *pm = f.pm1 + ((size_t)r * f.W + q / f.NPW) * (size_t)f.Tpad + f.shift;
+        hot = 0u;
+        for (int b = 0; b < nb; ++b)
+          if (pm[ts[b]] >= f.gm1[ts[b] + f.shift] - f.thr) hot |= 1u << b;
+        if (!hot) continue;
+      }
       double acc[SLOW_BATCH];
       for (int b = 0; b < SLOW_BATCH; ++b) acc[b] = 0.0;
       for (int s = 0; s < e.S; ++s) {
@@ -960,10 +983,12 @@ __global__ void __launch_bounds__(128) k_slow(ExactParams e, const int *slow_lis
         const long long tau = (long long)e.tmin[m] + e.tau16[m * e.NB + q];
         const double *row = e.on64 + (size_t)s * e.row_stride + e.origin + tau;
 #pragma unroll
-        for (int b = 0; b < SLOW_BATCH; ++b) acc[b] += row[ts[b]];
+        for (int b = 0; b < SLOW_BATCH; ++b)
+          if ((hot >> b) & 1u) acc[b] += row[ts[b]];
       }
 #pragma unroll
       for (int b = 0; b < SLOW_BATCH; ++b) {
+        if (!((hot >> b) & 1u)) continue;
         const double c = exp(acc[b] / avail);
         if (c > best[b] || (c == best[b] && (unsigned long long)gi < bidx[b])) { best[b] = c; bidx[b] = gi; }
       }
@@ -1419,8 +1444,13 @@ int scan_run_impl(qmb_ctx *ctx, qmb_lut *L, qmb_onsets *O, int32_t fsmp, int32_t
   double *pv = ctx->slow_val.p, *mv = pv + (size_t)slow_ctas * SLOW_CAP;
   unsigned long long *pi = ctx->slow_idx.p, *mi = pi + (size_t)slow_ctas * SLOW_CAP;
   auto slow_round = [&](int skip) -> int {
+    // the scan's partial maxima are intact only until the check windows reuse their buffers
+    SlowFilter f = {};
+    if (skip == 0 && !getenv("QMB_SLOW_NOFILTER")) {
+      f.pm1 = p.pm1; f.gm1 = G.m1; f.Tpad = p.Tpad; f.R = R; f.W = W; f.NPW = L->v.NPW; f.shift = shift; f.thr = thr;
+    }
     k_slow_compact<<<1, 1024, 0, ctx->stream>>>(ctx->slow_flag.p, T, skip, SLOW_CAP, ctx->slow_list.p, ctx->status.p);
-    k_slow<<<slow_ctas, 128, 0, ctx->stream>>>(e, ctx->slow_list.p, SLOW_CAP, (double)available, L->nodeidx.p,
+    k_slow<<<slow_ctas, 128, 0, ctx->stream>>>(e, f, ctx->slow_list.p, SLOW_CAP, (double)available, L->nodeidx.p,
                                                L->n_tiles, pv, pi);
     k_slow_merge<<<SLOW_CAP / 128, 128, 0, ctx->stream>>>(pv, pi, slow_ctas, SLOW_CAP, ctx->slow_list.p, mv, mi);
     ctx->launches += 3;

@@ -286,6 +286,37 @@ def test_near_ties_below_fp32_resolution(engine, n_levels, jitter):
     lut.free()
 
 
+def test_slow_path_partial_maximum_filter(engine, monkeypatch):
+    """
+    The all-node float64 re-scan only walks node subsets whose partial maximum of the scan reaches
+    m1 - thr.  Same input with the filter off (QMB_SLOW_NOFILTER=1): identical results, both equal
+    to the oracle; several node ranges and tiles so that the filter really discards subsets.
+    """
+    grid, S, T, fsmp, lsmp = (24, 20, 18), 6, 700, 4, 30
+    rng = np.random.default_rng(77)
+    levels = np.array([0.5, 0.8, 1.3])
+    total = fsmp + T + lsmp
+    onsets = levels[rng.integers(0, 3, size=(S, total))] * (1.0 + 1e-9 * rng.integers(0, 4, size=(S, total)))
+    ix, iy, iz = np.meshgrid(*[np.arange(g) for g in grid], indexing="ij")
+    tau = np.stack([np.round(0.7 * np.sqrt((ix - 3 * s) ** 2 + (iy - 2 * s) ** 2 + (iz + s) ** 2))
+                    for s in range(S)], axis=-1).astype(np.int32)
+    assert tau.max() <= lsmp
+    lut = engine.upload_lut(tau)
+    dev_on = engine.upload_onsets(onsets)
+    info = engine.detect_device(lut, dev_on, fsmp, lsmp, S)
+    got = engine.detect_fetch(T)
+    assert info["slow_samples"] > 0
+    monkeypatch.setenv("QMB_SLOW_NOFILTER", "1")
+    info2 = engine.detect_device(lut, dev_on, fsmp, lsmp, S)
+    got2 = engine.detect_fetch(T)
+    assert info2["slow_samples"] == info["slow_samples"]
+    for a, b in zip(got, got2):
+        np.testing.assert_array_equal(a, b)
+    want = O.find_max_coa(O.migrate(onsets, tau, fsmp, lsmp, S, threads=2), threads=2)
+    _check_detect(got, want)
+    lut.free()
+
+
 def test_span_too_wide_is_an_error_not_a_fallback(engine):
     """Travel-time range inside one tile beyond what shared memory can stage -> QMB_ERR_UNSUPPORTED."""
     from quakemigrate_b200.core import QmbError
