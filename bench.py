@@ -442,8 +442,14 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=CTRL_GROUP)
         dev_total_ms, e2e_sec, scan_mean, wall, tail_mean, slow = [float(x) for x in t]
         slow = int(slow)
+        # per-rank means: a rank's tail includes its wait for the slowest rank's scan at the exchange
+        mine = torch.tensor([float(np.mean(scan_ms)), float(np.mean(tail_ms))], dtype=torch.float64)
+        every = [torch.zeros(2, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(every, mine, group=CTRL_GROUP)
+        per_rank = {"scan_ms": [round(float(x[0]), 2) for x in every], "tail_ms": [round(float(x[1]), 2) for x in every]}
     else:
         scan_mean, tail_mean = float(np.mean(scan_ms)), float(np.mean(tail_ms))
+        per_rank = None
     ms_per_step = dev_total_ms / args.steps
     value = N_global * T / (ms_per_step * 1e-3)
 
@@ -510,6 +516,7 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
         "wall_s_timed_region": wall,
         "slow_path_samples": slow,
         "tail_ms_per_step": tail_mean,
+        "per_rank": per_rank,
         "scan": {"operand_bytes": scan_info["operand_bytes"], "operand_bits": scan_info["operand_bits"],
                  "fell_back_fp32": scan_info["fell_back_fp32"],
                  "check_windows": scan_info["check_windows"], "check_samples": scan_info["check_samples"],

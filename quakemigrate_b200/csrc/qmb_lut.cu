@@ -176,9 +176,14 @@ struct Region {
   int x0, y0, z0, x1, y1, z1;
 };
 
+// The widest tile decides how much shared memory a pipeline stage takes for the whole table (its
+// travel-time range sets the staged row length), so a shape is also kept compact: no edge longer
+// than 8 nodes unless that costs more than a quarter more slots than the best elongated shape
+// (a single z-column can only be cut into 1x1xNB pieces).
 void best_shape(int NB, int bx, int by, int bz, int &sx, int &sy, int &sz) {
-  long long best_vol = -1;
-  int best_sum = 0;
+  constexpr int LONGEST = 8;
+  long long best_vol[2] = {-1, -1};  // [0] any shape, [1] compact shapes
+  int best_sum[2] = {0, 0}, shape[2][3] = {{1, 1, NB}, {1, 1, NB}};
   for (int a = 1; a <= NB; ++a) {
     if (NB % a) continue;
     for (int b = 1; b <= NB / a; ++b) {
@@ -186,11 +191,16 @@ void best_shape(int NB, int bx, int by, int bz, int &sx, int &sy, int &sz) {
       const int c = NB / a / b;
       const long long vol = (long long)((bx + a - 1) / a) * a * ((by + b - 1) / b) * b * ((bz + c - 1) / c) * c;
       const int sum = a + b + c;
-      if (best_vol < 0 || vol < best_vol || (vol == best_vol && sum < best_sum)) {
-        best_vol = vol; best_sum = sum; sx = a; sy = b; sz = c;
-      }
+      const bool compact = a <= LONGEST && b <= LONGEST && c <= LONGEST;
+      for (int k = 0; k < (compact ? 2 : 1); ++k)
+        if (best_vol[k] < 0 || vol < best_vol[k] || (vol == best_vol[k] && sum < best_sum[k])) {
+          best_vol[k] = vol; best_sum[k] = sum;
+          shape[k][0] = a; shape[k][1] = b; shape[k][2] = c;
+        }
     }
   }
+  const int k = (best_vol[1] >= 0 && 4 * best_vol[1] <= 5 * best_vol[0]) ? 1 : 0;
+  sx = shape[k][0]; sy = shape[k][1]; sz = shape[k][2];
 }
 
 void tile_region(const Region &r, int sx, int sy, int sz, std::vector<int> &boxes) {

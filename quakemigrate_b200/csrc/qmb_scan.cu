@@ -978,13 +978,28 @@ __global__ void __launch_bounds__(128) k_slow(ExactParams e, SlowFilter f, const
       }
       double acc[SLOW_BATCH];
       for (int b = 0; b < SLOW_BATCH; ++b) acc[b] = 0.0;
-      for (int s = 0; s < e.S; ++s) {
-        const size_t m = (size_t)j * e.Spad + s;
-        const long long tau = (long long)e.tmin[m] + e.tau16[m * e.NB + q];
-        const double *row = e.on64 + (size_t)s * e.row_stride + e.origin + tau;
+      // four rows' table look-ups and gathers in flight at a time (the walk is latency-bound); the
+      // additions stay in row order like the reference's
+      for (int s0 = 0; s0 < e.S; s0 += 4) {
+        const double *row[4];
 #pragma unroll
-        for (int b = 0; b < SLOW_BATCH; ++b)
-          if ((hot >> b) & 1u) acc[b] += row[ts[b]];
+        for (int u = 0; u < 4; ++u) {
+          const int s = min(s0 + u, e.S - 1);
+          const size_t m = (size_t)j * e.Spad + s;
+          const long long tau = (long long)e.tmin[m] + e.tau16[m * e.NB + q];
+          row[u] = e.on64 + (size_t)s * e.row_stride + e.origin + tau;
+        }
+        double v[4][SLOW_BATCH];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int b = 0; b < SLOW_BATCH; ++b) v[u][b] = ((hot >> b) & 1u) ? row[u][ts[b]] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (s0 + u < e.S) {
+#pragma unroll
+            for (int b = 0; b < SLOW_BATCH; ++b) acc[b] += v[u][b];
+          }
       }
 #pragma unroll
       for (int b = 0; b < SLOW_BATCH; ++b) {
