@@ -309,6 +309,44 @@ def preprocess_stage(eng, cfg, prob, args, peak, peak_src):
 
 
 
+def timestep_chain_stage(eng, cfg, prob, lut, S):
+    """
+    One detect timestep as QuakeScan._continuous_compute runs it (scan.py:434-462), from RAW traces
+    in host memory to the integer channels ScanmSEED stores (io/scanmseed.py:102-130): H2D of the
+    trace block, pre_process (stalta.py:203-209), STA/LTA + onset rows (stalta.py:364-470), the
+    scan, the output stage, D2H of COA / COA_N / X / Y / Z.  Wall clock between device
+    synchronisations; shows what the stages either side of the scan cost next to it.  Timing
+    only: band-passing the synthetic traces changes the onset values, not the work.
+    """
+    from quakemigrate_b200 import preprocess as pp
+
+    sos = pp.butter_sos("bandpass", (2.0, 16.0), cfg.sampling_rate, 2)
+    h = cfg.node_spacing_km
+    T = cfg.n_samples
+    rows = []
+    for _ in range(3):
+        eng.sync()
+        t0 = time.perf_counter()
+        raw = eng.upload_waveforms(prob.waveforms)
+        flt = eng.filter_waveforms(raw, sos)
+        dev = eng.onsets_from_device_waveforms(flt, prob.row_channels, prob.nsta, prob.nlta, position=cfg.position)
+        eng.sync()
+        t1 = time.perf_counter()
+        eng.detect_device(lut, dev, prob.fsmp, prob.lsmp, S)
+        eng.sync()
+        t2 = time.perf_counter()
+        out = eng.detect_fetch_quantised(T, cfg.grid, (0.0, 0.0, 0.0), (h, h, h), 1e3)
+        t3 = time.perf_counter()
+        rows.append((t1 - t0, t2 - t1, t3 - t2))
+        raw.free(); flt.free(); dev.free()
+    a = np.median(np.array(rows[1:]), axis=0) * 1e3
+    return {"what": "raw host traces -> H2D -> pre_process -> STA/LTA onset rows -> scan -> output stage -> host int32 channels",
+            "before_scan_ms": float(a[0]), "scan_ms": float(a[1]), "output_stage_ms": float(a[2]),
+            "total_ms": float(a.sum()), "h2d_bytes": int(prob.waveforms.nbytes),
+            "d2h_bytes": int(sum(v.nbytes for v in out.values())),
+            "note": "wall clock between device synchronisations, median of 2 after 1 warm-up, outside the timed region"}
+
+
 # ------------------------------------------------------------------------------------------------
 # parity of this run's result against the reference C, on random windows of the GLOBAL grid
 # ------------------------------------------------------------------------------------------------
@@ -526,7 +564,8 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
     }
 
     if rank == 0 and world == 1:
-        line["stages"] = {"preprocess": preprocess_stage(eng, cfg, prob, args, peak, peak_src)}
+        line["stages"] = {"preprocess": preprocess_stage(eng, cfg, prob, args, peak, peak_src),
+                          "timestep_chain": timestep_chain_stage(eng, cfg, prob, lut, S)}
     if rank == 0 and not args.no_cpu_baseline:
         # the GLOBAL table on rank 0's host (the reference needs all nodes)
         tt_global = prob.traveltimes if (x0 == 0 and x1 == nx) else syn.make_traveltimes(cfg)[0]

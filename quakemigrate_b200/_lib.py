@@ -151,6 +151,8 @@ SIGNATURES = {
     "qmb_map3d_gaufilt": (ctypes.c_int, [c_void_p, c_void_p, c_double, ctypes.POINTER(c_void_p)]),
     "qmb_map3d_peak_device": (ctypes.c_int, [c_void_p, c_void_p, ctypes.POINTER(c_int64),
                                              ctypes.POINTER(c_double), ctypes.POINTER(c_double)]),
+    "qmb_rbf_cubic_peak": (ctypes.c_int, [c_void_p, c_dPt, c_int32, c_int32, ctypes.POINTER(c_int64),
+                                          ctypes.POINTER(c_double)]),
     "qmb_map3d_window": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                         c_int32, c_dPt]),
     "qmb_map3d_covfit": (ctypes.c_int, [c_void_p, c_void_p, c_dPt, c_double, c_int32, c_dPt]),

@@ -688,6 +688,21 @@ class Engine:
         _lib.check(self._lib.qmb_covfit3d(self._h, m, *m.shape, sp, float(thresh), int(win or 0), out))
         return out[:3].copy(), out[3:].reshape(3, 3).copy()
 
+    def rbf_cubic_peak(self, weights, n: int, upscale: int = 10):
+        """
+        Peak of the cubic radial-basis interpolant on the ``upscale``-times finer window grid
+        (``QuakeScan._splineloc``, scan.py:789-809): ``weights`` are the ``n**3`` weights of scipy's
+        ``Rbf(..., function="cubic")`` for the window; returns (index triple into the fine grid as
+        ``np.unravel_index(np.nanargmax(coa_map_int), ...)`` gives it, value).
+        """
+        w = np.ascontiguousarray(weights, dtype=np.double).reshape(-1)
+        if w.size != n ** 3:
+            raise ValueError("weights must hold n**3 values")
+        idx, mx = c_int64(-1), ctypes.c_double(0.0)
+        _lib.check(self._lib.qmb_rbf_cubic_peak(self._h, w, int(n), int(upscale), ctypes.byref(idx), ctypes.byref(mx)))
+        m = (n - 1) * upscale + 1
+        return tuple(int(i) for i in np.unravel_index(idx.value, (m, m, m))), mx.value
+
     def upload_map(self, map3d: np.ndarray) -> DeviceMap:
         m = np.ascontiguousarray(map3d, dtype=np.double)
         if m.ndim != 3:

@@ -223,6 +223,35 @@ __global__ void k_map_window(const double *map, Dims d, int x0, int y0, int z0, 
   out[i] = map[((long long)(x0 + ix) * d.ny + (y0 + iy)) * d.nz + (z0 + iz)];
 }
 
+// Cubic radial-basis interpolant of an n^3 window evaluated on the `up`-times finer grid
+// (QuakeScan._splineloc, scan.py:776-804: scipy's Rbf(function="cubic") called on
+// meshgrid(linspace(0, n-1, (n-1)*up+1))).  Output point (a, b, c) and centre (a', b', c'), both in
+// C order, sit at the coordinates (b, a, c) -- numpy.meshgrid's default 'xy' indexing -- which only
+// fixes the order of the three squares inside the distance.  out[p] = sum_j w[j] * r_pj^3.
+__global__ void __launch_bounds__(128) k_rbf_cubic(const double *w, int n, int M, double step, double *out) {
+  extern __shared__ double sw[];
+  const int n3 = n * n * n;
+  for (int j = threadIdx.x; j < n3; j += blockDim.x) sw[j] = w[j];
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= M * M * M) return;
+  const int c = p % M, b = (p / M) % M, a = p / (M * M);
+  // numpy.linspace: arange(num) * step, the last sample replaced by the stop value
+  const double x = b == M - 1 ? (double)(n - 1) : b * step;
+  const double y = a == M - 1 ? (double)(n - 1) : a * step;
+  const double z = c == M - 1 ? (double)(n - 1) : c * step;
+  double acc = 0.0;
+  int j = 0;
+  for (int ca = 0; ca < n; ++ca)
+    for (int cb = 0; cb < n; ++cb)
+      for (int cc = 0; cc < n; ++cc, ++j) {
+        const double dx = x - cb, dy = y - ca, dz = z - cc;
+        const double r = sqrt(dx * dx + dy * dy + dz * dz);
+        acc += r * r * r * sw[j];
+      }
+  out[p] = acc;
+}
+
 int check_map(qmb_ctx *ctx, qmb_map3d *m) {
   if (!ctx || !m) QMB_FAIL(QMB_ERR_ARG, "null argument");
   if (m->ctx != ctx) QMB_FAIL(QMB_ERR_ARG, "map belongs to a different context");
@@ -294,6 +323,32 @@ extern "C" int qmb_map3d_peak_device(qmb_ctx_t ctx, qmb_map3d_t m, int64_t *argm
   if (argmax) *argmax = h.idx;
   if (maxval) *maxval = h.mx;
   if (mean) *mean = h.cnt > 0 ? h.sum / (double)h.cnt : NAN;
+  return QMB_OK;
+}
+
+// Peak of the cubic RBF interpolant on the upscaled window grid (scan.py:801-809): `weights` are the
+// n^3 interpolation weights (the solution of scipy's Rbf system, C order of the window); returns the
+// first arg-max (C order of the (M, M, M) fine grid, M = (n - 1) * upscale + 1) and its value.
+extern "C" int qmb_rbf_cubic_peak(qmb_ctx_t ctx, const double *weights, int32_t n, int32_t upscale, int64_t *argmax,
+                                  double *maxval) {
+  if (!ctx || !weights || !argmax) QMB_FAIL(QMB_ERR_ARG, "null argument");
+  if (n < 2 || n > 16 || upscale < 1 || upscale > 64) QMB_FAIL(QMB_ERR_ARG, "bad window (%d) or upscale (%d)", n, upscale);
+  QMB_CUDA(cudaSetDevice(ctx->device));
+  const int M = (n - 1) * upscale + 1, n3 = n * n * n;
+  const long long total = (long long)M * M * M;
+  MapScratch s;
+  QMB_TRY(map_scratch(ctx, total, n3, s));
+  QMB_CUDA(cudaMemcpyAsync(s.taps, weights, sizeof(double) * n3, cudaMemcpyHostToDevice, ctx->stream));
+  const double step = (double)(n - 1) / (double)(M - 1);
+  k_rbf_cubic<<<(int)((total + 127) / 128), 128, sizeof(double) * n3, ctx->stream>>>(s.taps, n, M, step, s.a);
+  ctx->launches++;
+  QMB_CUDA(cudaGetLastError());
+  QMB_TRY(peak_of(ctx, s.a, total, s.part, s.peak));
+  PeakPartial h;
+  QMB_CUDA(cudaMemcpyAsync(&h, s.peak, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  QMB_CUDA(cudaStreamSynchronize(ctx->stream));
+  *argmax = h.idx;
+  if (maxval) *maxval = h.mx;
   return QMB_OK;
 }
 

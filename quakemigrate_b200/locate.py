@@ -31,11 +31,13 @@ def _window(shape, ijk, win):
     return lo, hi
 
 
-def spline_location_window(trim: np.ndarray, lo, ijk, win: int = 5, upscale: int = 10):
+def spline_location_window(trim: np.ndarray, lo, ijk, win: int = 5, upscale: int = 10, engine=None):
     """
     ``_splineloc`` (scan.py:736-841) on the window ``trim`` = ``coa_map[lo : lo + trim.shape]``:
     returns the fractional grid index of the interpolated peak, or the gridded peak when the
-    window touches the grid edge or the result leaves the window.
+    window touches the grid edge or the result leaves the window.  With an ``engine`` that has
+    ``rbf_cubic_peak`` the interpolation weights come from scipy's ``Rbf`` (a 125 x 125 solve) and
+    the dense evaluation on the 41^3 fine grid plus its arg-max run on the device.
     """
     from scipy.interpolate import Rbf
 
@@ -49,10 +51,14 @@ def spline_location_window(trim: np.ndarray, lo, ijk, win: int = 5, upscale: int
     # (scan.py:777, :797) and flattens the data in C order; reproduce exactly that pairing.
     xog, yog, zog = np.meshgrid(*axes)
     rbf = Rbf(xog.flatten(), yog.flatten(), zog.flatten(), trim.flatten(), function="cubic")
-    fine = [np.linspace(0, n - 1, (n - 1) * upscale + 1) for n in trim.shape]
-    xxg, yyg, zzg = np.meshgrid(*fine)
-    interp = rbf(xxg.flatten(), yyg.flatten(), zzg.flatten()).reshape(xxg.shape)
-    peak = np.array(np.unravel_index(np.nanargmax(interp), interp.shape)) / upscale + np.array(lo)
+    if engine is not None and hasattr(engine, "rbf_cubic_peak"):
+        fine_idx, _ = engine.rbf_cubic_peak(rbf.nodes, ext[0], upscale)
+    else:
+        fine = [np.linspace(0, n - 1, (n - 1) * upscale + 1) for n in trim.shape]
+        xxg, yyg, zzg = np.meshgrid(*fine)
+        interp = rbf(xxg.flatten(), yyg.flatten(), zzg.flatten()).reshape(xxg.shape)
+        fine_idx = np.unravel_index(np.nanargmax(interp), interp.shape)
+    peak = np.array(fine_idx) / upscale + np.array(lo)
     w2 = (win - 1) // 2
     if np.any(np.abs(ijk - peak) > w2):
         logging.info("\t !!!! Spline error: location outside interpolation window !!!!")
@@ -130,10 +136,10 @@ def calculate_location_device(coa_map_sum, lut, return_maps: bool = False, engin
     expect, cov = coa.covfit(lut.node_spacing, thresh=0.90)
     if engine_timer is not None:
         engine_timer()
-    spline_idx = spline_location_window(trim, lo, ijk)
+    spline_idx = spline_location_window(trim, lo, ijk, engine=getattr(coa_map_sum, "engine", None))
     gau_idx, gau_sigma = gaussian_fit_window(sub, lo7, s_ijk, s_mean)
     out = _finish(lut, spline_idx, gau_idx, gau_sigma, expect, cov, ijk)
-    out["pcie_bytes"] = int(2 * 32 + trim.nbytes + sub.nbytes + 12 * 8 + 2 * 7 * 8)
+    out["pcie_bytes"] = int(2 * 32 + trim.nbytes + sub.nbytes + 12 * 8 + 2 * 7 * 8 + trim.nbytes + 16)
     if return_maps:
         out["coa_map"], out["smoothed"] = coa.fetch(), smoothed.fetch()
     smoothed.free()

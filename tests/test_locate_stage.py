@@ -82,3 +82,36 @@ def test_cuda_map_stage_matches_reference(tag):
     np.testing.assert_allclose(e_w, e_r, rtol=1e-12)
     np.testing.assert_allclose(cov_w, cov_r, rtol=1e-9, atol=1e-14)
     eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_cuda_rbf_cubic_peak_matches_scipy(seed):
+    """
+    The dense evaluation of _splineloc's interpolant (scan.py:789-809) on the device against scipy's
+    Rbf called exactly as the reference calls it: same fine-grid arg-max, peak value to rounding --
+    on smooth peaks off the node centres (the locate case) and on rough random windows.
+    """
+    from scipy.interpolate import Rbf
+    from quakemigrate_b200.core import Engine
+    eng = Engine(0)
+    rng = np.random.default_rng(seed)
+    n, up = 5, 10
+    g = np.arange(n) - 2.0
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    c = rng.uniform(-0.45, 0.45, 3)
+    windows = [np.exp(-((X - c[0]) ** 2 / 2.5 + (Y - c[1]) ** 2 / 3.5 + (Z - c[2]) ** 2 / 1.7)),
+               rng.uniform(0.0, 1.0, (n, n, n))]
+    for trim in windows:
+        axes = [np.linspace(0, n - 1, n)] * 3
+        xo, yo, zo = np.meshgrid(*axes)
+        rbf = Rbf(xo.flatten(), yo.flatten(), zo.flatten(), trim.flatten(), function="cubic")
+        fine = [np.linspace(0, n - 1, (n - 1) * up + 1)] * 3
+        xx, yy, zz = np.meshgrid(*fine)
+        dense = rbf(xx.flatten(), yy.flatten(), zz.flatten()).reshape(xx.shape)
+        want = tuple(int(i) for i in np.unravel_index(np.nanargmax(dense), dense.shape))
+        got, val = eng.rbf_cubic_peak(rbf.nodes, n, up)
+        assert val == pytest.approx(dense.max(), rel=1e-11)
+        # a different fine node only if it ties with scipy's to rounding
+        assert got == want or dense[got] == pytest.approx(dense.max(), rel=1e-12)
+    eng.close()
