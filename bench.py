@@ -637,13 +637,14 @@ def run_locate(args, rank: int, world: int, local_rank: int, dist):
         dist.barrier()
     sampler.start()
     launches0 = eng.launch_count
-    dev_ms, scan_ms = [], []
+    dev_ms, scan_ms, span_total_ms = [], [], []
     for _ in range(args.steps):
         eng.flush_l2()
         eng.timer_start()
         out, loc = event(dev_on)
         dev_ms.append(out["device_ms"])
         scan_ms.append(out["scan"]["scan_ms"])
+        span_total_ms.append(out["scan"]["total_ms"])
     eng.sync()
     if world > 1:
         dist.barrier()
@@ -661,17 +662,20 @@ def run_locate(args, rank: int, world: int, local_rank: int, dist):
     # ---- e2e: host onsets in, location out (H2D of the onsets, host fits included) ---------------
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     Engine.pin(onsets_lin)
-    t_e2e = []
+    t_e2e, t_up = [], []
     for i in range(e2e_steps + 1):
         eng.sync()
         t0 = time.perf_counter()
         d = eng.upload_onsets(onsets_lin)
+        eng.sync()
+        t1 = time.perf_counter()
         eng.timer_start()
         out, loc = event(d)
         d.free()
         eng.sync()
         if i:
             t_e2e.append(time.perf_counter() - t0)
+            t_up.append(t1 - t0)
     Engine.unpin(onsets_lin)
     e2e_sec = float(np.mean(t_e2e))
     dev_total_ms = float(np.sum(dev_ms))
@@ -728,6 +732,10 @@ def run_locate(args, rank: int, world: int, local_rank: int, dist):
                           "frac": ga * bpg / (smem_peak * 4), "sm_mhz_used": sm_mhz},
         },
         "stages": {
+            "e2e_steps_s": [round(float(v), 4) for v in t_e2e],
+            "e2e_onset_upload_and_row_preparation_s": [round(float(v), 4) for v in t_up],
+            "timed_steps_device_ms": [round(float(v), 2) for v in dev_ms],
+            "timed_steps_span_scan_ms": [round(float(v), 2) for v in span_total_ms],
             "span_pass_ms": float(st[0]), "window_pass_ms": float(st[1]), "device_map_stage_ms": float(st[2]),
             "host_fits_ms": float(st[3]),
             "note": "wall clock between device synchronisations, measured outside the timed region",
