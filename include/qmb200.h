@@ -262,8 +262,9 @@ int qmb_preprocess(qmb_ctx_t ctx, const double *x, int32_t n_channels, int64_t n
                    int32_t decimate, double *out /* (n_channels, ceil(n / decimate)) */);
 
 /* np.abs(scipy.signal.hilbert(x, axis=-1)) of a host (n_channels, n) block: the envelope behind the
- * "env" / "env_squared" transforms (stalta.py:520-523).  The FFTs are cuFFT's (dlopen'ed on first
- * use); weighting and modulus are this library's kernels. */
+ * "env" / "env_squared" transforms (stalta.py:520-523).  A DFT of exactly the trace length like
+ * scipy's, by this library's own transforms: Bluestein's chirp-z convolution on power-of-two
+ * Stockham FFT passes (no FFT library). */
 int qmb_envelope(qmb_ctx_t ctx, const double *x, int32_t n_channels, int64_t n, double *out);
 
 /* batched STA/LTA on (n_channels, n) host arrays; `onset` must arrive pre-filled like the

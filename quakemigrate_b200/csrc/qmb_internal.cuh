@@ -132,10 +132,10 @@ struct qmb_ctx {
   DevBuf<double> map_scratch;   // locate 3-D map stage: convolution ping-pong, reductions, taps
   DevBuf<double> pp_scratch;    // pre-processing: stats, matrix powers, chunk/tile states, pass-1 output
   DevBuf<int> pp_sel;           // pre-processing: selected channel indices
-  // Hilbert envelopes: cached cuFFT plan pair (handles are ints) and complex scratch
-  int fft_fwd = 0, fft_inv = 0, fft_batch = 0;
-  int64_t fft_n = 0, fft_idist = 0;
-  DevBuf<double> fft_buf;
+  // Hilbert envelopes (own Bluestein + Stockham transforms, qmb_envelope.cu)
+  int64_t fft_n = 0;          // trace length the cached chirp / chirp filter belong to
+  DevBuf<double> fft_buf;     // two complex work buffers of the envelope transform
+  DevBuf<double> fft_chirp;   // [w (n)][transformed chirp filter (M)][scratch (M)] complex
   struct qmb_onsets *tmp_onsets = nullptr;  // onset rows of the one-call qmb_detect (reused)
   int32_t last_n_samples = 0;
 };

@@ -171,9 +171,13 @@ def test_stalta_onset_with_bandpass_filters_matches_the_reference_chain(eng):
     assert onset_data.device_onsets is not None and sum(onset_data.availability.values()) == 8
 
 
-@pytest.mark.parametrize("n", [2, 7, 64, 1001, 4096, 30011, 137460])
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 16, 17, 64, 1001, 4096, 4097, 30011, 65536, 137460, 409260])
 def test_envelope_matches_scipy_hilbert(eng, n):
-    """|analytic signal| for even / odd / prime / composite lengths (137460 = cfg2's row length)."""
+    """
+    |analytic signal| for even / odd / prime / composite / power-of-two lengths (137460 and 409260 are
+    cfg2's and cfg3's row lengths): the library's own Bluestein + Stockham transforms against scipy's
+    exact-length FFT.
+    """
     rng = np.random.default_rng(n)
     x = _traces(rng, 3, n, trend=False)
     _close(eng.envelope(x), PO.envelope(x), rtol=1e-11)
