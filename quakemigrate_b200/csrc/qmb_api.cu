@@ -173,6 +173,7 @@ extern "C" int qmb_ctx_destroy(qmb_ctx_t ctx) {
   ctx->slow_val.release(); ctx->slow_idx.release(); ctx->flush.release(); ctx->stage_lin.release();
   ctx->q_i32.release(); ctx->q_f64.release(); ctx->map_scratch.release(); ctx->pp_scratch.release(); ctx->pp_sel.release();
   qmb_fft_release(ctx);
+  qmb_map_pool_clear(ctx);
   if (ctx->tmp_onsets) {
     ctx->tmp_onsets->log32.release(); ctx->tmp_onsets->log64.release(); ctx->tmp_onsets->rowmax.release();
     ctx->tmp_onsets->q16.release(); ctx->tmp_onsets->qrange.release();

@@ -263,5 +263,6 @@ int qmb_preprocess_device(qmb_ctx *ctx, const double *d_x, int64_t x_stride, con
 int qmb_envelope_device(qmb_ctx *ctx, const double *d_x, int64_t x_stride, int32_t n_channels, int64_t n,
                         double *d_out, int64_t out_stride);
 void qmb_fft_release(qmb_ctx *ctx);
+void qmb_map_pool_clear(const qmb_ctx *ctx);  // return the recycled map buffers of a context (qmb_locate.cu)
 qmb_ctx *qmb_default_ctx();
 int qmb_map3d_new(qmb_ctx *ctx, int32_t nx, int32_t ny, int32_t nz, qmb_map3d **out);
