@@ -323,15 +323,20 @@ def timestep_chain_stage(eng, cfg, prob, lut, S):
     sos = pp.butter_sos("bandpass", (2.0, 16.0), cfg.sampling_rate, 2)
     h = cfg.node_spacing_km
     T = cfg.n_samples
-    rows = []
+    rows, parts = [], []
     for _ in range(3):
         eng.sync()
         t0 = time.perf_counter()
         raw = eng.upload_waveforms(prob.waveforms)
+        eng.sync()
+        ta = time.perf_counter()
         flt = eng.filter_waveforms(raw, sos)
+        eng.sync()
+        tb = time.perf_counter()
         dev = eng.onsets_from_device_waveforms(flt, prob.row_channels, prob.nsta, prob.nlta, position=cfg.position)
         eng.sync()
         t1 = time.perf_counter()
+        parts.append((ta - t0, tb - ta, t1 - tb))
         eng.detect_device(lut, dev, prob.fsmp, prob.lsmp, S)
         eng.sync()
         t2 = time.perf_counter()
@@ -340,8 +345,11 @@ def timestep_chain_stage(eng, cfg, prob, lut, S):
         rows.append((t1 - t0, t2 - t1, t3 - t2))
         raw.free(); flt.free(); dev.free()
     a = np.median(np.array(rows[1:]), axis=0) * 1e3
+    b = np.median(np.array(parts[1:]), axis=0) * 1e3
     return {"what": "raw host traces -> H2D -> pre_process -> STA/LTA onset rows -> scan -> output stage -> host int32 channels",
-            "before_scan_ms": float(a[0]), "scan_ms": float(a[1]), "output_stage_ms": float(a[2]),
+            "before_scan_ms": float(a[0]),
+            "before_scan_parts_ms": {"h2d_pageable": float(b[0]), "pre_process": float(b[1]), "onset_rows": float(b[2])},
+            "scan_ms": float(a[1]), "output_stage_ms": float(a[2]),
             "total_ms": float(a.sum()), "h2d_bytes": int(prob.waveforms.nbytes),
             "d2h_bytes": int(sum(v.nbytes for v in out.values())),
             "note": "wall clock between device synchronisations, median of 2 after 1 warm-up, outside the timed region"}

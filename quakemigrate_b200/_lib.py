@@ -12,13 +12,15 @@ missing or no B200 is visible, calls raise.
 from __future__ import annotations
 
 import ctypes
+import os
 import pathlib
 
 import numpy as np
 import numpy.ctypeslib as clib
 
 _HERE = pathlib.Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libqmb200.so"
+# QMB_LIB: load another build of the library (tuning experiments); default the in-tree one
+LIB_PATH = pathlib.Path(os.environ["QMB_LIB"]) if os.environ.get("QMB_LIB") else _HERE / "libqmb200.so"
 
 c_int32 = ctypes.c_int32
 c_int64 = ctypes.c_int64

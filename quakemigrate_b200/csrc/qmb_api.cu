@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <vector>
 
 #include "qmb_internal.cuh"
 
@@ -30,6 +31,85 @@ extern "C" int qmb_device_count(int *count) {
   *count = 0;
   QMB_CUDA(cudaGetDeviceCount(count));
   return QMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// recycled device buffers (see DevBuf in qmb_internal.cuh)
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct PoolEntry {
+  int device;
+  size_t bytes;
+  void *p;
+};
+std::mutex g_pool_mu;
+std::vector<PoolEntry> g_pool;
+size_t g_pool_bytes = 0;
+constexpr size_t POOL_MIN_BYTES = 1u << 20;
+constexpr size_t POOL_MAX_ENTRIES = 32;
+size_t pool_cap_bytes() {
+  static const size_t cap = [] {
+    const char *env = getenv("QMB_POOL_MB");
+    const long long mb = env ? atoll(env) : 8192;
+    return (size_t)(mb < 0 ? 0 : mb) << 20;
+  }();
+  return cap;
+}
+}  // namespace
+
+void *qmb_pool_take(size_t bytes) {
+  if (bytes < POOL_MIN_BYTES) return nullptr;
+  int device = -1;
+  if (cudaGetDevice(&device) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(g_pool_mu);
+  for (size_t i = 0; i < g_pool.size(); ++i)
+    if (g_pool[i].device == device && g_pool[i].bytes == bytes) {
+      void *p = g_pool[i].p;
+      g_pool_bytes -= bytes;
+      g_pool.erase(g_pool.begin() + i);
+      return p;
+    }
+  return nullptr;
+}
+
+bool qmb_pool_give(void *p, size_t bytes) {
+  if (!p || bytes < POOL_MIN_BYTES || bytes > pool_cap_bytes()) return false;
+  int device = -1;
+  if (cudaGetDevice(&device) != cudaSuccess) return false;
+  // like cudaFree: nothing queued on the buffer survives the hand-back
+  if (cudaDeviceSynchronize() != cudaSuccess) return false;
+  std::lock_guard<std::mutex> lock(g_pool_mu);
+  // make room: drop the oldest entries (they are the least likely to be asked for again)
+  while (!g_pool.empty() && (g_pool.size() >= POOL_MAX_ENTRIES || g_pool_bytes + bytes > pool_cap_bytes())) {
+    if (g_pool[0].device == device) cudaFree(g_pool[0].p);
+    else {
+      cudaSetDevice(g_pool[0].device);
+      cudaFree(g_pool[0].p);
+      cudaSetDevice(device);
+    }
+    g_pool_bytes -= g_pool[0].bytes;
+    g_pool.erase(g_pool.begin());
+  }
+  g_pool.push_back({device, bytes, p});
+  g_pool_bytes += bytes;
+  return true;
+}
+
+void qmb_pool_clear(int device) {
+  int cur = -1;
+  cudaGetDevice(&cur);
+  std::lock_guard<std::mutex> lock(g_pool_mu);
+  for (size_t i = 0; i < g_pool.size();) {
+    if (g_pool[i].device == device) {
+      cudaSetDevice(device);
+      cudaFree(g_pool[i].p);
+      g_pool_bytes -= g_pool[i].bytes;
+      g_pool.erase(g_pool.begin() + i);
+    } else {
+      ++i;
+    }
+  }
+  if (cur >= 0) cudaSetDevice(cur);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -173,13 +253,13 @@ extern "C" int qmb_ctx_destroy(qmb_ctx_t ctx) {
   ctx->slow_val.release(); ctx->slow_idx.release(); ctx->flush.release(); ctx->stage_lin.release();
   ctx->q_i32.release(); ctx->q_f64.release(); ctx->map_scratch.release(); ctx->pp_scratch.release(); ctx->pp_sel.release();
   qmb_fft_release(ctx);
-  qmb_map_pool_clear(ctx);
   if (ctx->tmp_onsets) {
     ctx->tmp_onsets->log32.release(); ctx->tmp_onsets->log64.release(); ctx->tmp_onsets->rowmax.release();
     ctx->tmp_onsets->q16.release(); ctx->tmp_onsets->qrange.release();
     delete ctx->tmp_onsets;
     ctx->tmp_onsets = nullptr;
   }
+  qmb_pool_clear(ctx->device);
   for (int i = 0; i < 4; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   for (int i = 0; i < 2; ++i)

@@ -63,22 +63,38 @@ constexpr int QMB_DEFAULT_QGROUP = 2;  // 15-bit rows, two rows per carry-free g
 // ---------------------------------------------------------------------------------------------
 // device buffer helper (RAII-free; owned by the structs below)
 // ---------------------------------------------------------------------------------------------
+// Recycling of large device buffers (qmb_api.cu): the handles a detect / locate loop creates and
+// frees every timestep or event (trace blocks, onset rows, maps) have the same sizes every time, and
+// cudaMalloc / cudaFree of hundreds of MB cost milliseconds to tens of milliseconds each and
+// serialise against every other driver call.  A freed buffer of >= 1 MiB is kept (after a device
+// synchronise, which cudaFree implies as well, so it carries no pending work) and handed to the
+// next request of exactly that size on that device.  Bounded by QMB_POOL_MB (default 8192; 0: off)
+// and 32 entries; qmb_ctx_destroy returns the device's entries.
+void *qmb_pool_take(size_t bytes);
+bool qmb_pool_give(void *p, size_t bytes);
+void qmb_pool_clear(int device);
+
 template <typename T>
 struct DevBuf {
   T *p = nullptr;
   size_t n = 0;
+  bool pooled = false;  // recycle through qmb_pool_* (handle-owned buffers) instead of cudaFree
+  static DevBuf Pooled() {
+    DevBuf b;
+    b.pooled = true;
+    return b;
+  }
   int ensure(size_t count) {
     if (count <= n && p) return QMB_OK;
-    if (p) cudaFree(p);
-    p = nullptr;
-    n = 0;
+    release();
     if (count == 0) return QMB_OK;
-    QMB_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+    if (pooled) p = (T *)qmb_pool_take(count * sizeof(T));
+    if (!p) QMB_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
     n = count;
     return QMB_OK;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p && !(pooled && qmb_pool_give(p, n * sizeof(T)))) cudaFree(p);
     p = nullptr;
     n = 0;
   }
@@ -189,8 +205,8 @@ struct qmb_onsets {
   int64_t P = 0;          // samples per row as seen by the caller (fsmp + T + lsmp)
   int64_t stride = 0;     // device row stride in elements (multiple of 4)
   int64_t front = 0;      // leading pad elements (so that front + fsmp can be 16B-aligned)
-  DevBuf<float> log32;    // [S][stride]
-  DevBuf<double> log64;   // [S][stride]
+  DevBuf<float> log32 = DevBuf<float>::Pooled();     // [S][stride]
+  DevBuf<double> log64 = DevBuf<double>::Pooled();   // [S][stride]
   DevBuf<double> rowmax;  // [S] max |log onset| per row (for the fp32 error bound)
   double rowmax_sum = 0.0;  // host copy of sum(rowmax), taken when the rows are prepared
   std::vector<double> h_rowmax;
@@ -199,7 +215,7 @@ struct qmb_onsets {
   //   stream 0 ("even"): q16[(2 s + 0) * qstride + pos] = u(sample)
   //   stream 1 ("odd") : q16[(2 s + 1) * qstride + pos] = u(sample + 1)
   // so that the pair (u(i), u(i + 1)) is one aligned 32-bit word for every i.
-  DevBuf<uint16_t> q16;
+  DevBuf<uint16_t> q16 = DevBuf<uint16_t>::Pooled();
   DevBuf<double> qrange;  // [S][2] min / max of each row
   int64_t qstride = 0, qfront = 0;
   int32_t qG = 1, qbits = 16, qlevels = 65535;  // rows per carry-free group <-> bits per sample
@@ -210,7 +226,7 @@ struct qmb_map3d {  // float64 (nx, ny, nz) map resident on the device (locate 3
   qmb_ctx *ctx = nullptr;
   int device = 0;
   int32_t nx = 0, ny = 0, nz = 0;
-  DevBuf<double> v;
+  DevBuf<double> v = DevBuf<double>::Pooled();
 };
 
 struct qmb_waveforms {  // device-resident float64 traces, (C, n) C-order
@@ -218,7 +234,7 @@ struct qmb_waveforms {  // device-resident float64 traces, (C, n) C-order
   int device = 0;
   int32_t C = 0;
   int64_t n = 0;
-  DevBuf<double> data;
+  DevBuf<double> data = DevBuf<double>::Pooled();
 };
 
 constexpr int64_t QMB_ONSET_FRONT = 4;     // leading pad (elements); alignment slack
@@ -263,6 +279,5 @@ int qmb_preprocess_device(qmb_ctx *ctx, const double *d_x, int64_t x_stride, con
 int qmb_envelope_device(qmb_ctx *ctx, const double *d_x, int64_t x_stride, int32_t n_channels, int64_t n,
                         double *d_out, int64_t out_stride);
 void qmb_fft_release(qmb_ctx *ctx);
-void qmb_map_pool_clear(const qmb_ctx *ctx);  // return the recycled map buffers of a context (qmb_locate.cu)
 qmb_ctx *qmb_default_ctx();
 int qmb_map3d_new(qmb_ctx *ctx, int32_t nx, int32_t ny, int32_t nz, qmb_map3d **out);

@@ -19,8 +19,6 @@
 
 #include <vector>
 
-#include <mutex>
-
 #include "qmb_internal.cuh"
 
 namespace {
@@ -266,50 +264,11 @@ int check_map(qmb_ctx *ctx, qmb_map3d *m) {
 // ---------------------------------------------------------------------------------------------
 // device-resident maps
 // ---------------------------------------------------------------------------------------------
-// Map buffers are recycled: a located event allocates two maps (marginal, smoothed) and frees them
-// again, and cudaMalloc / cudaFree of tens of MB cost milliseconds each and serialise against every
-// other driver call of the process.  Up to four freed buffers per process are kept and handed back
-// to the context that freed them (exact size match; reuse is then ordered by that context's
-// stream); qmb_map_pool_clear() returns a context's buffers when it is destroyed.
-namespace {
-struct PooledMap {
-  const void *owner;  // context whose stream orders the buffer's pending work (a key, never dereferenced)
-  int device;
-  size_t n;
-  double *p;
-};
-std::mutex g_map_pool_mu;
-std::vector<PooledMap> g_map_pool;
-}  // namespace
-
-void qmb_map_pool_clear(const qmb_ctx *ctx) {
-  std::lock_guard<std::mutex> lock(g_map_pool_mu);
-  for (size_t i = 0; i < g_map_pool.size();) {
-    if (g_map_pool[i].owner == ctx) {
-      cudaSetDevice(g_map_pool[i].device);
-      cudaFree(g_map_pool[i].p);
-      g_map_pool.erase(g_map_pool.begin() + i);
-    } else {
-      ++i;
-    }
-  }
-}
-
 int qmb_map3d_new(qmb_ctx *ctx, int32_t nx, int32_t ny, int32_t nz, qmb_map3d **out) {
   *out = nullptr;
   if (nx <= 0 || ny <= 0 || nz <= 0) QMB_FAIL(QMB_ERR_ARG, "bad map shape");
   qmb_map3d *m = new qmb_map3d();
   m->ctx = ctx; m->device = ctx->device; m->nx = nx; m->ny = ny; m->nz = nz;
-  {
-    std::lock_guard<std::mutex> lock(g_map_pool_mu);
-    for (size_t i = 0; i < g_map_pool.size(); ++i)
-      if (g_map_pool[i].owner == ctx && g_map_pool[i].device == ctx->device && g_map_pool[i].n == (size_t)nx * ny * nz) {
-        m->v.p = g_map_pool[i].p;
-        m->v.n = g_map_pool[i].n;
-        g_map_pool.erase(g_map_pool.begin() + i);
-        break;
-      }
-  }
   const int rc = m->v.ensure((size_t)nx * ny * nz);
   if (rc != QMB_OK) {
     delete m;
@@ -346,14 +305,6 @@ extern "C" int qmb_map3d_fetch(qmb_map3d_t m, double *host) {
 extern "C" int qmb_map3d_free(qmb_map3d_t m) {
   if (!m) return QMB_OK;
   cudaSetDevice(m->device);
-  {
-    std::lock_guard<std::mutex> lock(g_map_pool_mu);
-    if (m->v.p && g_map_pool.size() < 4) {
-      g_map_pool.push_back({m->ctx, m->device, m->v.n, m->v.p});
-      m->v.p = nullptr;
-      m->v.n = 0;
-    }
-  }
   m->v.release();
   delete m;
   return QMB_OK;

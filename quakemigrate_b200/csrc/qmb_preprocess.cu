@@ -34,8 +34,14 @@
 
 namespace {
 
-constexpr int PP_L = 32;                 // samples per chunk = per thread
-constexpr int PP_TPB = 256;              // chunks (threads) per tile
+#ifndef QMB_PP_L
+#define QMB_PP_L 32
+#endif
+#ifndef QMB_PP_TPB
+#define QMB_PP_TPB 256
+#endif
+constexpr int PP_L = QMB_PP_L;           // samples per chunk = per thread
+constexpr int PP_TPB = QMB_PP_TPB;       // chunks (threads) per tile
 constexpr int PP_TILE = PP_L * PP_TPB;   // samples per tile / CTA
 constexpr int PP_MAX_SEC = 4;            // second-order sections per filter (template instances)
 constexpr double PP_PI = 3.14159265358979323846;
