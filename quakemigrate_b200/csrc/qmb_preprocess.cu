@@ -400,7 +400,6 @@ __global__ void __launch_bounds__(PP_TPB) k_sos_fused(PreParams p, FusedScratch 
   double *z_s = tin_s + D;                      // D: the tile's aggregate
   double *R = z_s + D;                          // D * PP_L
   __shared__ int s_ticket;
-  __shared__ double wtot[(PP_TPB / 32) * D];
   const int t = threadIdx.x;
   if (t == 0) s_ticket = atomicAdd(f.ticket, 1);
   for (int i = t; i < D * PP_L; i += PP_TPB) R[i] = f.resp[i];
@@ -415,60 +414,31 @@ __global__ void __launch_bounds__(PP_TPB) k_sos_fused(PreParams p, FusedScratch 
   double *my = tile + t * (PP_L + 1);
 #pragma unroll 4
   for (int k = 0; k < PP_L; ++k) my[k] = cascade_step<NSEC>(p.coef, st, my[k]);
-  // 2. inclusive scan over the chunks of the tile: shuffles inside a warp (no barriers), the warp
-  // totals chained through shared memory, then the carry of the earlier warps advanced to this chunk
-  {
-    const int lane = t & 31, w = t >> 5;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      double prev[D];
-#pragma unroll
-      for (int d = 0; d < D; ++d) prev[d] = __shfl_up_sync(0xffffffffu, st[d], o);
-      if (lane >= o) {
-        const double *M = p.mpow + (size_t)o * D * D;
-#pragma unroll
-        for (int i = 0; i < D; ++i) {
-          double acc = 0.0;
-#pragma unroll
-          for (int j = 0; j < D; ++j) acc += M[i * D + j] * prev[j];
-          st[i] += acc;
-        }
-      }
-    }
-    if (lane == 31) {
-#pragma unroll
-      for (int d = 0; d < D; ++d) wtot[w * D + d] = st[d];
-    }
+  for (int d = 0; d < D; ++d) sv[t * D + d] = st[d];
+  // 2. inclusive scan over the chunks of the tile
+  for (int o = 1; o < PP_TPB; o <<= 1) {
     __syncthreads();
-    if (w > 0) {
-      // state at the end of warp w - 1 (zero state at the tile start): C <- M^32 C + total(v)
-      const double *M32 = p.mpow + (size_t)32 * D * D;
-      double carry[D];
-#pragma unroll
-      for (int d = 0; d < D; ++d) carry[d] = wtot[d];
-      for (int v = 1; v < w; ++v) {
-        double nx[D];
-#pragma unroll
-        for (int i = 0; i < D; ++i) {
-          double acc = wtot[v * D + i];
-#pragma unroll
-          for (int j = 0; j < D; ++j) acc += M32[i * D + j] * carry[j];
-          nx[i] = acc;
-        }
-#pragma unroll
-        for (int d = 0; d < D; ++d) carry[d] = nx[d];
-      }
-      const double *M = p.mpow + (size_t)(lane + 1) * D * D;  // through this warp's chunks 0 .. lane
+    double add[D];
+    if (t >= o) {
+      const double *M = p.mpow + (size_t)o * D * D;
+      const double *prev = sv + (t - o) * D;
 #pragma unroll
       for (int i = 0; i < D; ++i) {
         double acc = 0.0;
 #pragma unroll
-        for (int j = 0; j < D; ++j) acc += M[i * D + j] * carry[j];
-        st[i] += acc;
+        for (int j = 0; j < D; ++j) acc += M[i * D + j] * prev[j];
+        add[i] = acc;
       }
     }
+    __syncthreads();
+    if (t >= o) {
 #pragma unroll
-    for (int d = 0; d < D; ++d) sv[t * D + d] = st[d];
+      for (int i = 0; i < D; ++i) {
+        st[i] += add[i];
+        sv[t * D + i] = st[i];
+      }
+    }
   }
   __syncthreads();
   double c0[D];  // state at the start of this chunk, given a zero state at the start of the tile
