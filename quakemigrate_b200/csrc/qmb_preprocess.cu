@@ -460,37 +460,49 @@ __global__ void __launch_bounds__(PP_TPB) k_sos_fused(PreParams p, FusedScratch 
     double acc[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) acc[d] = 0.0;
+    // everything that does not depend on the predecessors is fetched before the first poll, so the
+    // critical path of the look-back is one round trip to the descriptors, not three
+    double Prow[D];
+#pragma unroll
+    for (int q = 0; q < D; ++q) Prow[q] = lane < D ? p.mpow[(size_t)PP_TPB * D * D + lane * D + q] : 0.0;
     bool done = T == 0;
     for (int base = 0; !done; base += 32) {
       const int dist = base + lane, j = T - 1 - dist;
-      double v[D];
+      constexpr bool PREFETCH_P = D <= 4;  // 16 values; 36 or 64 would spill
+      double v[D], Pd[PREFETCH_P ? D * D : 1];
       bool incl = false;
       if (j >= 0) {
-        const DescEntry *e = f.desc + (row + j) * 2 * D;
-        for (;;) {  // the inclusive state if it is there, else the aggregate, else wait
-          bool ok = true;
+        if constexpr (PREFETCH_P) {
 #pragma unroll
-          for (int q = 0; q < D; ++q) ok &= desc_load(e + D + q, v[q]);
-          if (ok) {
+          for (int q = 0; q < D * D; ++q) Pd[q] = f.ppow[(size_t)dist * D * D + q];
+        }
+        const DescEntry *e = f.desc + (row + j) * 2 * D;
+        for (;;) {  // the inclusive state if it is there, else the aggregate, else wait; one round trip per poll
+          double vi[D];
+          bool ok_i = true, ok_a = true;
+#pragma unroll
+          for (int q = 0; q < D; ++q) ok_i &= desc_load(e + D + q, vi[q]);
+#pragma unroll
+          for (int q = 0; q < D; ++q) ok_a &= desc_load(e + q, v[q]);
+          if (ok_i) {
+#pragma unroll
+            for (int q = 0; q < D; ++q) v[q] = vi[q];
             incl = true;
             break;
           }
-          ok = true;
-#pragma unroll
-          for (int q = 0; q < D; ++q) ok &= desc_load(e + q, v[q]);
-          if (ok) break;
+          if (ok_a) break;
         }
       }
       const unsigned has_incl = __ballot_sync(0xffffffffu, incl);
       const int k = has_incl ? __ffs(has_incl) - 1 : 32;  // nearest tile of this window with a known end state
       if (j >= 0 && lane <= k) {
         // in[T] = sum_{d < dist_k} P^d z_{T-1-d} + P^dist_k E_{T-1-dist_k}
-        const double *Pd = f.ppow + (size_t)dist * D * D;
+        const double *Pg = f.ppow + (size_t)dist * D * D;
 #pragma unroll
         for (int i = 0; i < D; ++i) {
           double a2 = 0.0;
 #pragma unroll
-          for (int q = 0; q < D; ++q) a2 += Pd[i * D + q] * v[q];
+          for (int q = 0; q < D; ++q) a2 += (PREFETCH_P ? Pd[i * D + q] : Pg[i * D + q]) * v[q];
           acc[i] += a2;
         }
       }
@@ -500,10 +512,9 @@ __global__ void __launch_bounds__(PP_TPB) k_sos_fused(PreParams p, FusedScratch 
     for (int d = 0; d < D; ++d)
       for (int o = 16; o > 0; o >>= 1) acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], o);
     if (lane < D) {  // lane i: component i of the inclusive end state P in + z
-      const double *P = p.mpow + (size_t)PP_TPB * D * D;
       double e = z_s[lane];
 #pragma unroll
-      for (int q = 0; q < D; ++q) e += P[lane * D + q] * acc[q];
+      for (int q = 0; q < D; ++q) e += Prow[q] * acc[q];
       desc_store(mine + D + lane, e);
     }
     if (lane == 0) {
