@@ -115,3 +115,48 @@ def test_cuda_rbf_cubic_peak_matches_scipy(seed):
         # a different fine node only if it ties with scipy's to rounding
         assert got == want or dense[got] == pytest.approx(dense.max(), rel=1e-12)
     eng.close()
+
+
+def test_spline_window_with_a_device_style_peak_evaluator():
+    """
+    locate.spline_location_window hands the dense evaluation to ``engine.rbf_cubic_peak`` when the
+    engine has it.  A numpy restatement of the kernel's index arithmetic (csrc/qmb_locate.cu,
+    k_rbf_cubic: output (a, b, c) and centre (a', b', c') at the coordinates (b, a, c), linspace
+    steps, first arg-max in C order) stands in for the device: both routes give the same location
+    on smooth off-centre peaks, so the coordinate pairing of the reference's meshgrid calls
+    (scan.py:777-804) is what the kernel reproduces.
+    """
+    from quakemigrate_b200 import locate
+
+    class _Eng:
+        calls = 0
+
+        def rbf_cubic_peak(self, weights, n, upscale=10):
+            type(self).calls += 1
+            m = (n - 1) * upscale + 1
+            step = (n - 1) / (m - 1)
+            fine = np.arange(m) * step
+            fine[-1] = n - 1
+            a, b, c = np.meshgrid(fine, fine, fine, indexing="ij")      # output index (a, b, c)
+            ca, cb, cc = [v.reshape(-1) for v in np.meshgrid(*[np.arange(n, dtype=float)] * 3, indexing="ij")]
+            w = np.asarray(weights).reshape(-1)
+            out = np.zeros(a.shape)
+            for j in range(n ** 3):
+                dx, dy, dz = b - cb[j], a - ca[j], c - cc[j]
+                r = np.sqrt(dx * dx + dy * dy + dz * dz)
+                out += r * r * r * w[j]
+            flat = int(np.argmax(out))
+            return tuple(int(i) for i in np.unravel_index(flat, out.shape)), float(out.reshape(-1)[flat])
+
+    rng = np.random.default_rng(5)
+    g = np.arange(5) - 2.0
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    for _ in range(4):
+        c = rng.uniform(-0.45, 0.45, 3)
+        trim = np.exp(-((X - c[0]) ** 2 / 2.5 + (Y - c[1]) ** 2 / 3.5 + (Z - c[2]) ** 2 / 1.7))
+        lo, ijk = [10, 20, 30], [12, 22, 32]
+        host = locate.spline_location_window(trim, lo, ijk)
+        dev = locate.spline_location_window(trim, lo, ijk, engine=_Eng())
+        np.testing.assert_array_equal(host, dev)
+        np.testing.assert_allclose(host - np.array(ijk), c, atol=0.11)     # the fine grid is 0.1 node wide
+    assert _Eng.calls == 4
