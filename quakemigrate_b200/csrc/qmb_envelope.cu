@@ -11,7 +11,8 @@
 //     last one), one kernel per pass, ping-pong between two buffers.  Thread i of a pass with
 //     p = product of the earlier radices:  k = i mod p,  u[r] = x[i + r*T] * e^(-+2 pi i r k / (p R)),
 //     v = DFT_R(u) in registers (radix-2 butterflies, bit-reversed order), y[(i - k) R + k + s p] = v[s].
-//     Reads are coalesced; a thread's R stores cover p-strided elements (whole sectors once p >= 2).
+//     Reads are coalesced; a thread's R stores are p elements apart, coalesced across the warp for
+//     p >= 32; the first pass (p = 1, 16 consecutive results per thread) goes through shared memory.
 //   * arbitrary N by Bluestein's chirp-z identity  n k = (n^2 + k^2 - (k - n)^2) / 2:
 //         DFT_N(a)[k] = conj(w[k]) * sum_n a[n] conj(w[n]) w[k - n],   w[m] = e^(i pi m^2 / N),
 //     i.e. a circular convolution of length M = 2^ceil(log2(2N-1)) done with the FFT above; the
@@ -40,8 +41,9 @@ __device__ __constant__ double TW16_S[8] = {0.0, 0.38268343236508977, 0.70710678
 // One Stockham pass of radix R = 2^LR over `batch` transforms of length M (blockIdx.y = transform).
 // sign = -1: forward (e^-), +1: inverse (unnormalised).  `mul` (nullable, length M): the result is
 // multiplied element-wise by it on the way out (the chirp filter after the last forward pass).
+constexpr int FFT_TPB = 128;
 template <int LR>
-__global__ void __launch_bounds__(128) k_fft_pass(const cplx *__restrict__ x, cplx *__restrict__ y, int log2M, int p,
+__global__ void __launch_bounds__(FFT_TPB) k_fft_pass(const cplx *__restrict__ x, cplx *__restrict__ y, int log2M, int p,
                                                   double sign, const cplx *__restrict__ mul) {
   constexpr int R = 1 << LR;
   const long long M = 1LL << log2M, T = M >> LR;
@@ -77,6 +79,31 @@ __global__ void __launch_bounds__(128) k_fft_pass(const cplx *__restrict__ x, cp
         const int q = t * (8 / span);  // angle 2 pi t / (2 span) = 2 pi q / 16
         u[base + t + span] = q == 0 ? d : cmul(d, make_double2(TW16_C[q], sign * TW16_S[q]));
       }
+    }
+  }
+  if constexpr (LR == 4) {
+    // First pass of a transform (p = 1): a thread's 16 results are 16 consecutive elements, so the
+    // warp's stores would stride 256 bytes.  Transpose through shared memory (rows padded to 17
+    // elements: conflict-free 16-byte accesses) and write the block's 2048 elements coalesced.
+    if (p == 1 && (T % FFT_TPB) == 0) {
+      extern __shared__ double2 stage[];
+#pragma unroll
+      for (int pos = 0; pos < R; ++pos) {
+        int s = 0;
+#pragma unroll
+        for (int b = 0; b < LR; ++b) s |= ((pos >> b) & 1) << (LR - 1 - b);
+        stage[threadIdx.x * (R + 1) + s] = u[pos];
+      }
+      __syncthreads();
+      const long long base = (long long)blockIdx.x * FFT_TPB * R;
+#pragma unroll
+      for (int m = 0; m < R; ++m) {
+        const int e = threadIdx.x + FFT_TPB * m;
+        const cplx v = stage[(e >> LR) * (R + 1) + (e & (R - 1))];
+        const long long o = base + e;
+        yb[o] = mul ? cmul(v, mul[o]) : v;
+      }
+      return;
     }
   }
 #pragma unroll
@@ -167,13 +194,13 @@ int fft_pow2(qmb_ctx *ctx, cplx *a, cplx *b, int log2M, int batch, double sign, 
   while (rem > 0) {
     const int LR = rem >= 4 ? 4 : rem;
     const long long T = (1LL << log2M) >> LR;
-    const dim3 grid((unsigned)((T + 127) / 128), (unsigned)batch);
+    const dim3 grid((unsigned)((T + FFT_TPB - 1) / FFT_TPB), (unsigned)batch);
     const cplx *m = (rem == LR) ? mul : nullptr;
     switch (LR) {
-      case 4: k_fft_pass<4><<<grid, 128, 0, ctx->stream>>>(src, dst, log2M, p, sign, m); break;
-      case 3: k_fft_pass<3><<<grid, 128, 0, ctx->stream>>>(src, dst, log2M, p, sign, m); break;
-      case 2: k_fft_pass<2><<<grid, 128, 0, ctx->stream>>>(src, dst, log2M, p, sign, m); break;
-      default: k_fft_pass<1><<<grid, 128, 0, ctx->stream>>>(src, dst, log2M, p, sign, m); break;
+      case 4: k_fft_pass<4><<<grid, FFT_TPB, sizeof(cplx) * FFT_TPB * 17, ctx->stream>>>(src, dst, log2M, p, sign, m); break;
+      case 3: k_fft_pass<3><<<grid, FFT_TPB, 0, ctx->stream>>>(src, dst, log2M, p, sign, m); break;
+      case 2: k_fft_pass<2><<<grid, FFT_TPB, 0, ctx->stream>>>(src, dst, log2M, p, sign, m); break;
+      default: k_fft_pass<1><<<grid, FFT_TPB, 0, ctx->stream>>>(src, dst, log2M, p, sign, m); break;
     }
     ctx->launches++;
     QMB_CUDA(cudaGetLastError());
