@@ -14,7 +14,6 @@ Plain csv, no obspy / pandas needed to write; pinned byte-for-byte by the refere
 from __future__ import annotations
 
 import csv
-import pathlib
 
 from .scanmseed import _julday, _run_path, from_us, to_us
 
